@@ -1,0 +1,457 @@
+/*
+ * stereo_oracle.c -- CPU ORACLE (test infrastructure only; see stereo_oracle.h).
+ *
+ * Plain-C restatement of the reference pthreads path.  Every function cites the
+ * reference file:line it follows (paths relative to /root/reference).
+ * Build: see oracle/Makefile (-O3 -ffp-contract=off, no -march=native, no fast-math:
+ * the reference builds with plain -O3 on baseline x86-64, CMakeLists.txt:17, so no
+ * FMA contraction happens there either).
+ */
+#define _GNU_SOURCE
+#include "stereo_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ------------------------------------------------------------------ utilities */
+
+/* ComFunc.h:67-71 get_rt(): CLOCK_MONOTONIC; kept in double here (the reference
+ * truncates to float, which is only a precision loss of the timer itself). */
+static double now_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec * 1e3 + (double)ts.tv_nsec * 1e-6;
+}
+
+/* cv::BORDER_REFLECT_101 index map (gfedcb|abcdefgh|gfedcba) */
+static inline int reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        else i = 2 * (n - 1) - i;
+    }
+    return i;
+}
+
+/* ------------------------------------------------------------------ a1: input scaling */
+
+/* StereoMatch.cpp:193-197: lFrame.convertTo(lFrame, CV_32F, 1 / 255.0f)
+ * OpenCV cvtScale 8u->32f works in float: (float)u * (float)alpha (+0). */
+void orc_u8_to_f32(const uint8_t* src, float* dst, size_t n)
+{
+    const float alpha = 1 / 255.0f;
+    for (size_t i = 0; i < n; ++i) dst[i] = (float)src[i] * alpha;
+}
+
+/* ------------------------------------------------------------------ a2: CVC::preprocess */
+
+/* CVC.cpp:43 cv::cvtColor(Img, GrdX, CV_RGB2GRAY).  OpenCV RGB2Gray<float>: coefficient
+ * 0.299f on channel 0, 0.587f on channel 1, 0.114f on channel 2 (the reference feeds a BGR
+ * image, so 0.299 lands on blue -- replicated, not fixed). */
+void orc_rgb2gray(const float* img3, int W, int H, float* gray, int gray_mode)
+{
+    const size_t n = (size_t)W * H;
+    if (gray_mode == 0) {
+        for (size_t i = 0; i < n; ++i) {
+            const float c0 = img3[3 * i], c1 = img3[3 * i + 1], c2 = img3[3 * i + 2];
+            gray[i] = fmaf(c2, 0.114f, fmaf(c0, 0.299f, c1 * 0.587f));
+        }
+    } else {
+        for (size_t i = 0; i < n; ++i) {
+            const float c0 = img3[3 * i], c1 = img3[3 * i + 1], c2 = img3[3 * i + 2];
+            gray[i] = (c0 * 0.299f + c1 * 0.587f) + c2 * 0.114f;
+        }
+    }
+}
+
+/* CVC.cpp:44 cv::Sobel(GrdX, GrdX, CV_32F, 1, 0, 1): ksize=1, dx=1 -> kernel [-1 0 1],
+ * BORDER_REFLECT_101 (so columns 0 and W-1 are exactly 0). */
+void orc_sobel_x(const float* gray, int W, int H, float* grdx)
+{
+    for (int y = 0; y < H; ++y) {
+        const float* g = gray + (size_t)y * W;
+        float* o = grdx + (size_t)y * W;
+        for (int x = 0; x < W; ++x) {
+            const float r = g[reflect101(x + 1, W)];
+            const float l = g[reflect101(x - 1, W)];
+            o[x] = r - l;
+        }
+    }
+}
+
+/* CVC.cpp:41-46 */
+void orc_cvc_preprocess(const float* img3, int W, int H, float* grdx, int gray_mode)
+{
+    float* gray = (float*)malloc((size_t)W * H * sizeof(float));
+    orc_rgb2gray(img3, W, H, gray, gray_mode);
+    orc_sobel_x(gray, W, H, grdx);
+    free(gray);
+}
+
+/* ------------------------------------------------------------------ a3/a4: myCostGrd */
+
+/* CVC.cpp:18-27: all-float arithmetic (math.h in C++ gives fabs(float) -> float). */
+static inline float cost_grd4(const float* lC, const float* rC, const float* lG, const float* rG)
+{
+    float clrDiff = fabsf(lC[0] - rC[0]) + fabsf(lC[1] - rC[1]) + fabsf(lC[2] - rC[2]);
+    float grdDiff = fabsf(*lG - *rG);
+    return 0.9f * clrDiff + (1 - 0.9f) * grdDiff; /* ALPHA_32F 0.9f, CVC.h:22 */
+}
+
+/* CVC.cpp:30-39: BC_32F is the double literal 1.0 (CVC.h:12), so the differences, fabs and
+ * the three-term sum are evaluated in double and rounded to float once per assignment. */
+static inline float cost_grd2(const float* lC, const float* lG)
+{
+    float clrDiff = (float)(fabs((double)lC[0] - 1.0) + fabs((double)lC[1] - 1.0) + fabs((double)lC[2] - 1.0));
+    float grdDiff = (float)fabs((double)*lG - 1.0);
+    return 0.9f * clrDiff + (1 - 0.9f) * grdDiff;
+}
+
+/* ------------------------------------------------------------------ a5/a6: buildCV */
+
+/* CVC.cpp:122-149 */
+void orc_buildcv_left(const float* lImg, const float* rImg, const float* lGrd, const float* rGrd,
+                      int W, int H, int d, float* cost)
+{
+    for (int y = 0; y < H; ++y) {
+        const float* lData = lImg + (size_t)y * W * 3;
+        const float* rData = rImg + (size_t)y * W * 3;
+        const float* lGData = lGrd + (size_t)y * W;
+        const float* rGData = rGrd + (size_t)y * W;
+        float* c = cost + (size_t)y * W;
+        for (int x = d; x < W; ++x)
+            c[x] = cost_grd4(lData + 3 * x, rData + 3 * (x - d), lGData + x, rGData + x - d);
+        for (int x = 0; x < d && x < W; ++x)
+            c[x] = cost_grd2(lData + 3 * x, lGData + x);
+    }
+}
+
+/* CVC.cpp:151-179 */
+void orc_buildcv_right(const float* lImg, const float* rImg, const float* lGrd, const float* rGrd,
+                       int W, int H, int d, float* cost)
+{
+    int border = W - d;
+    if (border < 0) border = 0;
+    for (int y = 0; y < H; ++y) {
+        const float* lData = lImg + (size_t)y * W * 3;
+        const float* rData = rImg + (size_t)y * W * 3;
+        const float* lGData = lGrd + (size_t)y * W;
+        const float* rGData = rGrd + (size_t)y * W;
+        float* c = cost + (size_t)y * W;
+        for (int x = 0; x < border; ++x)
+            c[x] = cost_grd4(lData + 3 * x, rData + 3 * (x + d), lGData + x, rGData + x + d);
+        for (int x = border; x < W; ++x)
+            c[x] = cost_grd2(lData + 3 * x, lGData + x);
+    }
+}
+
+/* ------------------------------------------------------------------ a10: cv::boxFilter 8x8 */
+
+/* OpenCV box filter for CV_32F, normalize=true, ksize 8x8, default anchor (4,4),
+ * BORDER_REFLECT_101.  Restates modules/imgproc/src/box_filter.simd.hpp:
+ *   RowSum<float,double>:   s = sum of first 8 (double); then s += (double)S[i+8] - (double)S[i]
+ *   ColumnSum<double,float>: s0 = SUM + newest; dst = (float)(s0 * (1.0/64)); SUM = s0 - oldest
+ * Rows are padded 4 left / 3 right, the column pass sees rows y-4 .. y+3 (reflected). */
+void orc_box8(const float* src, int W, int H, float* dst)
+{
+    const int K = ORC_GIF_R_WIN, AL = 4;
+    const double scale = 1.0 / (double)(K * K);
+    const int PW = W + K - 1;
+    float* prow = (float*)malloc((size_t)PW * sizeof(float));
+    double* rs = (double*)malloc((size_t)W * H * sizeof(double)); /* row sums of every source row */
+    double* SUM = (double*)calloc((size_t)W, sizeof(double));
+
+    for (int y = 0; y < H; ++y) {
+        const float* s = src + (size_t)y * W;
+        for (int i = 0; i < PW; ++i) prow[i] = s[reflect101(i - AL, W)];
+        double* D = rs + (size_t)y * W;
+        double acc = 0;
+        for (int i = 0; i < K; ++i) acc += (double)prow[i];
+        D[0] = acc;
+        for (int i = 0; i < W - 1; ++i) {
+            acc += (double)prow[i + K] - (double)prow[i];
+            D[i + 1] = acc;
+        }
+    }
+    /* column pass; padded row index r = y' + 4 maps to source row reflect101(y', H) */
+    for (int r = 0; r < K - 1; ++r) {
+        const double* Sp = rs + (size_t)reflect101(r - AL, H) * W;
+        for (int i = 0; i < W; ++i) SUM[i] += Sp[i];
+    }
+    float* out = dst;
+    float* tmp = NULL;
+    if (src == dst) { tmp = (float*)malloc((size_t)W * H * sizeof(float)); out = tmp; }
+    for (int y = 0; y < H; ++y) {
+        const double* Sp = rs + (size_t)reflect101(y + K - 1 - AL, H) * W; /* newest: y+3 */
+        const double* Sm = rs + (size_t)reflect101(y - AL, H) * W;         /* oldest: y-4 */
+        float* D = out + (size_t)y * W;
+        for (int i = 0; i < W; ++i) {
+            double s0 = SUM[i] + Sp[i];
+            D[i] = (float)(s0 * scale);
+            SUM[i] = s0 - Sm[i];
+        }
+    }
+    if (tmp) { memcpy(dst, tmp, (size_t)W * H * sizeof(float)); free(tmp); }
+    free(SUM); free(rs); free(prow);
+}
+
+/* ------------------------------------------------------------------ a8: CVF::preprocess */
+
+/* CVF.cpp:44-70 */
+void orc_cvf_preprocess(const float* img3, int W, int H, float* rgb, float* mean, float* var)
+{
+    const size_t n = (size_t)W * H;
+    for (size_t i = 0; i < n; ++i)                 /* split(), CVF.cpp:47 */
+        for (int c = 0; c < 3; ++c) rgb[c * n + i] = img3[3 * i + c];
+    for (int c = 0; c < 3; ++c)                    /* CVF.cpp:49-51 */
+        orc_box8(rgb + c * n, W, H, mean + c * n);
+    float* tmp = (float*)malloc(n * sizeof(float));
+    int varIdx = 0;
+    for (int c = 0; c < 3; ++c) {                  /* CVF.cpp:60-69 */
+        for (int cp = c; cp < 3; ++cp) {
+            float* v = var + (size_t)varIdx * n;
+            for (size_t i = 0; i < n; ++i) tmp[i] = rgb[c * n + i] * rgb[cp * n + i];
+            orc_box8(tmp, W, H, v);
+            for (size_t i = 0; i < n; ++i) tmp[i] = mean[c * n + i] * mean[cp * n + i];
+            for (size_t i = 0; i < n; ++i) v[i] -= tmp[i];
+            ++varIdx;
+        }
+    }
+    free(tmp);
+}
+
+/* ------------------------------------------------------------------ a9: GuidedFilter_cv */
+
+/* CVF.cpp:72-165 */
+void orc_guided_filter(const float* rgb, const float* mean_I, const float* var_I, int W, int H,
+                       float* p, float* a_out, float* b_out)
+{
+    const size_t n = (size_t)W * H;
+    float* mean_p = (float*)malloc(n * sizeof(float));
+    float* tmp = (float*)malloc(n * sizeof(float));
+    float* mean_Ip = (float*)malloc(3 * n * sizeof(float)); /* becomes cov_Ip */
+    float* a = (float*)malloc(3 * n * sizeof(float));
+    float* q = (float*)malloc(n * sizeof(float));
+
+    orc_box8(p, W, H, mean_p);                                   /* CVF.cpp:81-82 */
+    for (int c = 0; c < 3; ++c) {                                /* CVF.cpp:86-89 */
+        for (size_t i = 0; i < n; ++i) tmp[i] = rgb[c * n + i] * p[i];
+        orc_box8(tmp, W, H, mean_Ip + c * n);
+    }
+    for (int c = 0; c < 3; ++c) {                                /* CVF.cpp:92-95 */
+        for (size_t i = 0; i < n; ++i) tmp[i] = mean_I[c * n + i] * mean_p[i];
+        for (size_t i = 0; i < n; ++i) mean_Ip[c * n + i] = mean_Ip[c * n + i] - tmp[i];
+    }
+    const float* cov = mean_Ip;
+    for (size_t i = 0; i < n; ++i) {                             /* CVF.cpp:102-149 */
+        float c0 = cov[i], c1 = cov[n + i], c2 = cov[2 * n + i];
+        float a11 = var_I[i] + ORC_GIF_EPS;
+        float a12 = var_I[n + i];
+        float a13 = var_I[2 * n + i];
+        float a21 = var_I[n + i];
+        float a22 = var_I[3 * n + i] + ORC_GIF_EPS;
+        float a23 = var_I[4 * n + i];
+        float a31 = var_I[2 * n + i];
+        float a32 = var_I[4 * n + i];
+        float a33 = var_I[5 * n + i] + ORC_GIF_EPS;
+        float DET = a11 * (a33 * a22 - a32 * a23) -
+                    a21 * (a33 * a12 - a32 * a13) +
+                    a31 * (a23 * a12 - a22 * a13);
+        DET = 1 / DET;
+        a[i] = DET * (
+            c0 * (a33 * a22 - a32 * a23) +
+            c1 * (a31 * a23 - a33 * a21) +
+            c2 * (a32 * a21 - a31 * a22));
+        a[n + i] = DET * (
+            c0 * (a32 * a13 - a33 * a12) +
+            c1 * (a33 * a11 - a31 * a13) +
+            c2 * (a31 * a12 - a32 * a11));
+        a[2 * n + i] = DET * (
+            c0 * (a23 * a12 - a22 * a13) +
+            c1 * (a21 * a13 - a23 * a11) +
+            c2 * (a22 * a11 - a21 * a12));
+    }
+    for (int c = 0; c < 3; ++c) {                                /* CVF.cpp:152-155 */
+        for (size_t i = 0; i < n; ++i) tmp[i] = a[c * n + i] * mean_I[c * n + i];
+        for (size_t i = 0; i < n; ++i) mean_p[i] -= tmp[i];
+    }
+    if (a_out) memcpy(a_out, a, 3 * n * sizeof(float));
+    if (b_out) memcpy(b_out, mean_p, n * sizeof(float));
+
+    orc_box8(mean_p, W, H, q);                                   /* CVF.cpp:157-158 */
+    for (int c = 0; c < 3; ++c) {                                /* CVF.cpp:159-163 */
+        orc_box8(a + c * n, W, H, tmp);
+        for (size_t i = 0; i < n; ++i) tmp[i] = tmp[i] * rgb[c * n + i];
+        for (size_t i = 0; i < n; ++i) q[i] += tmp[i];
+    }
+    memcpy(p, q, n * sizeof(float));                             /* CVF.cpp:38 in-place */
+    free(q); free(a); free(mean_Ip); free(tmp); free(mean_p);
+}
+
+/* ------------------------------------------------------------------ a12: WTA */
+
+/* DispSel.cpp:83-109: d from 1, strict <, minCost starts at (float)DBL_MAX = +inf */
+static void wta_rows(const float* vol, int W, int H, int D, uint8_t* disp, int y0, int y1)
+{
+    const size_t n = (size_t)W * H;
+    for (int y = y0; y < y1; ++y) {
+        for (int x = 0; x < W; ++x) {
+            float minCost = INFINITY;
+            int minDis = 0;
+            for (int d = 1; d < D; ++d) {
+                const float c = vol[(size_t)d * n + (size_t)y * W + x];
+                if (c < minCost) { minCost = c; minDis = d; }
+            }
+            disp[(size_t)y * W + x] = (uint8_t)minDis;
+        }
+    }
+}
+
+void orc_wta(const float* vol, int W, int H, int D, uint8_t* disp)
+{
+    wta_rows(vol, W, H, D, disp, 0, H);
+}
+
+/* ------------------------------------------------------------------ a7/a11: thread drivers */
+
+typedef struct {
+    int kind; /* 0 left cvc, 1 right cvc, 2 filter, 3 wta rows */
+    const float *lImg, *rImg, *lGrd, *rGrd;
+    const float *rgb, *mean, *var;
+    const float* vol_in;
+    float* slice;
+    uint8_t* disp;
+    int W, H, D, d, y0, y1;
+} task_t;
+
+static void* task_entry(void* arg)
+{
+    task_t* t = (task_t*)arg;
+    switch (t->kind) {
+    case 0: orc_buildcv_left(t->lImg, t->rImg, t->lGrd, t->rGrd, t->W, t->H, t->d, t->slice); break;
+    case 1: orc_buildcv_right(t->lImg, t->rImg, t->lGrd, t->rGrd, t->W, t->H, t->d, t->slice); break;
+    case 2: orc_guided_filter(t->rgb, t->mean, t->var, t->W, t->H, t->slice, NULL, NULL); break;
+    case 3: wta_rows(t->vol_in, t->W, t->H, t->D, t->disp, t->y0, t->y1); break;
+    }
+    return NULL;
+}
+
+/* DispEst.cpp:235-251 batching: for level in 0..=n/threads, block = threads or n%threads,
+ * create block pthreads (one per d), join them all, next level. */
+static int run_batched(task_t* tasks, int n, int threads)
+{
+    if (threads < 1) threads = 1;
+    pthread_t* th = (pthread_t*)malloc((size_t)n * sizeof(pthread_t));
+    for (int level = 0; level <= n / threads; ++level) {
+        int block = (level < n / threads) ? threads : (n % threads);
+        for (int it = 0; it < block; ++it) {
+            int d = level * threads + it;
+            if (pthread_create(&th[d], NULL, task_entry, &tasks[d]) != 0) { free(th); return -1; }
+        }
+        for (int it = 0; it < block; ++it) pthread_join(th[level * threads + it], NULL);
+    }
+    free(th);
+    return 0;
+}
+
+/* DispEst.cpp:222-270 */
+int orc_cost_const(const float* lImg, const float* rImg, int W, int H, int D, int threads,
+                   int gray_mode, float* lGrd, float* rGrd, float* lVol, float* rVol)
+{
+    const size_t n = (size_t)W * H;
+    orc_cvc_preprocess(lImg, W, H, lGrd, gray_mode);   /* DispEst.cpp:232 */
+    orc_cvc_preprocess(rImg, W, H, rGrd, gray_mode);   /* DispEst.cpp:233 */
+    task_t* tasks = (task_t*)calloc((size_t)D, sizeof(task_t));
+    for (int d = 0; d < D; ++d) {                      /* DispEst.cpp:243 */
+        task_t t = {0};
+        t.kind = 0; t.lImg = lImg; t.rImg = rImg; t.lGrd = lGrd; t.rGrd = rGrd;
+        t.W = W; t.H = H; t.d = d; t.slice = lVol + (size_t)d * n;
+        tasks[d] = t;
+    }
+    int rc = run_batched(tasks, D, threads);
+    for (int d = 0; d < D && rc == 0; ++d) {           /* DispEst.cpp:260: swapped arguments */
+        task_t t = {0};
+        t.kind = 1; t.lImg = rImg; t.rImg = lImg; t.lGrd = rGrd; t.rGrd = lGrd;
+        t.W = W; t.H = H; t.d = d; t.slice = rVol + (size_t)d * n;
+        tasks[d] = t;
+    }
+    if (rc == 0) rc = run_batched(tasks, D, threads);
+    free(tasks);
+    return rc;
+}
+
+/* Reconstructed CostFilter_CPU (declared DispEst.h:42, never defined): CVF::preprocess per
+ * view (CVF.cpp:44) then one filterCV_thread per d (CVF.cpp:28-41) in CostConst_CPU batches. */
+int orc_cost_filter(const float* lImg, const float* rImg, int W, int H, int D, int threads,
+                    float* lVol, float* rVol)
+{
+    const size_t n = (size_t)W * H;
+    float* g = (float*)malloc(12 * n * sizeof(float));
+    float *rgb = g, *mean = g + 3 * n, *var = g + 6 * n;
+    task_t* tasks = (task_t*)calloc((size_t)D, sizeof(task_t));
+    int rc = 0;
+    for (int view = 0; view < 2 && rc == 0; ++view) {
+        orc_cvf_preprocess(view == 0 ? lImg : rImg, W, H, rgb, mean, var);
+        float* vol = view == 0 ? lVol : rVol;
+        for (int d = 0; d < D; ++d) {
+            task_t t = {0};
+            t.kind = 2; t.rgb = rgb; t.mean = mean; t.var = var;
+            t.W = W; t.H = H; t.d = d; t.slice = vol + (size_t)d * n;
+            tasks[d] = t;
+        }
+        rc = run_batched(tasks, D, threads);
+    }
+    free(tasks); free(g);
+    return rc;
+}
+
+/* DispEst.cpp:311-321; DispSel::CVSelect is "#pragma omp parallel for" over rows
+ * (DispSel.cpp:88) -- rows are split over `threads` pthreads here. */
+static int wta_view(const float* vol, int W, int H, int D, uint8_t* dis, int threads)
+{
+    if (threads < 1) threads = 1;
+    if (threads > H) threads = H;
+    task_t* tasks = (task_t*)calloc((size_t)threads, sizeof(task_t));
+    for (int t = 0; t < threads; ++t) {
+        task_t k = {0};
+        k.kind = 3; k.vol_in = vol; k.W = W; k.H = H; k.D = D; k.disp = dis;
+        k.y0 = (int)((long)H * t / threads); k.y1 = (int)((long)H * (t + 1) / threads);
+        tasks[t] = k;
+    }
+    int rc = run_batched(tasks, threads, threads);
+    free(tasks);
+    return rc;
+}
+
+int orc_disp_select(const float* lVol, const float* rVol, int W, int H, int D,
+                    uint8_t* lDis, uint8_t* rDis)
+{
+    orc_wta(lVol, W, H, D, lDis);
+    orc_wta(rVol, W, H, D, rDis);
+    return 0;
+}
+
+int orc_pipeline(const float* lImg, const float* rImg, int W, int H, int D, int threads,
+                 int gray_mode, float* lVol, float* rVol, uint8_t* lDis, uint8_t* rDis,
+                 double* times_ms)
+{
+    const size_t n = (size_t)W * H;
+    float* lGrd = (float*)malloc(n * sizeof(float));
+    float* rGrd = (float*)malloc(n * sizeof(float));
+    double t0 = now_ms();
+    int rc = orc_cost_const(lImg, rImg, W, H, D, threads, gray_mode, lGrd, rGrd, lVol, rVol);
+    double t1 = now_ms();
+    if (rc == 0) rc = orc_cost_filter(lImg, rImg, W, H, D, threads, lVol, rVol);
+    double t2 = now_ms();
+    if (rc == 0) rc = wta_view(lVol, W, H, D, lDis, threads);
+    if (rc == 0) rc = wta_view(rVol, W, H, D, rDis, threads);
+    double t3 = now_ms();
+    if (times_ms) { times_ms[0] = t1 - t0; times_ms[1] = t2 - t1; times_ms[2] = t3 - t2; }
+    free(lGrd); free(rGrd);
+    return rc;
+}
