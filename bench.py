@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- disparity volumes/s of the STEREO_GIF hot path (CVC -> CVF -> WTA) on B200.
+
+Contract (see the task brief): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line
+on rank 0.  A "step" is one stereo frame through CostConst_GPU + CostFilter_GPU + DispSelect_GPU
+producing BOTH disparity maps.  Workload at every N: BASELINE config C4, synthetic 1920x1080, D=128,
+fp32.  N>1 (launched by torchrun, one rank per GPU): the disparity axis is sharded D/N slices per
+rank, one NCCL all-gather of packed per-pixel (cost,d) minima per view, then the final min -> u8 maps
+(strong scaling: the frame is fixed, `value` = frames/s of the whole job).
+
+  value : frames/s with the interleaved f32 images already resident in HBM (device-timed, CUDA events)
+  e2e   : same metric through the host-facing C-ABI calls: images in pinned HOST memory, H2D of both
+          images and D2H of both u8 maps inside the timed region
+  roofline : the fused CVF kernel's algorithmic bytes / its event-timed duration vs the measured HBM peak
+  cpu_baseline / --impl reference : the CPU oracle (C restatement of the reference's pthreads path;
+          the reference itself cannot be built here: no OpenCV C++ headers / CL/cl.h) on the host cores
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, D = 1920, 1080, 128
+WORKLOAD = "C4 synthetic 1920x1080 D=128 fp32, both views (lDisMap+rDisMap)"
+METRIC = "disparity_volumes_per_s"
+UNIT = "volumes/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def oracle_frame(l, r, threads, sample_slices=None):
+    """One frame (or a slice sample of it) through the CPU oracle -> seconds per FULL frame."""
+    from oracle import oracle as O
+    Ds = D if sample_slices is None else sample_slices
+    t0 = time.perf_counter()
+    res = O.pipeline(l, r, Ds, threads=threads)
+    dt = time.perf_counter() - t0
+    # per-slice cost is uniform (every slice is the same CVC + GIF work; WTA is 1% of the frame)
+    return dt * (D / Ds), res["times_ms"]
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path (oracle port) on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    from primestereomatch_b200 import synth
+    l, r, _ = synth.stereo_pair_f32(W, H, D)
+    cores = os.cpu_count() or 1
+    threads = min(cores, D)
+    n = args.steps + args.warmup
+    # bounded sample: the whole frame when the run is short, else a D/8-slice sample of it
+    sample = None if n <= 8 else max(8, D // 8)
+    for _ in range(args.warmup):
+        oracle_frame(l, r, threads, sample)
+    ts = []
+    for _ in range(args.steps):
+        t, _ = oracle_frame(l, r, threads, sample)
+        ts.append(t)
+    sec = float(np.mean(ts))
+    val = 1.0 / sec
+    what = "full frame" if sample is None else f"{sample} of {D} disparity slices of both views, scaled x{D / sample:g}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "threads": threads,
+                   "note": "CPU oracle = C restatement of the reference pthreads path (reference needs OpenCV+OpenCL headers: unbuildable here); "
+                           "threads = all host cores (the reference itself caps at MAX_CPU_THREADS=8)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": what},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cvf-mode", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from primestereomatch_b200 import DispEst, capi, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, (world, args.gpus)
+    warm = max(3, args.warmup)
+
+    L = capi.lib()
+    l, r, _ = synth.stereo_pair_f32(W, H, D)
+    lp = torch.from_numpy(l).pin_memory()
+    rp = torch.from_numpy(r).pin_memory()
+    ld_dev, rd_dev = lp.cuda(), rp.cuda()
+
+    d_count = D // world
+    d_begin = rank * d_count
+    if rank == world - 1:
+        d_count = D - d_begin
+    de = DispEst(l, r, D, 8, True, device=local_rank, d_begin=d_begin, d_count=d_count)
+    de.set_option(capi.PSM_OPT_CVF_MODE, args.cvf_mode)
+    de.set_option(capi.PSM_OPT_VARIANT, args.variant)
+    stream = torch.cuda.Stream()  # a real (non-default) stream: handle 0 would mean "context's own stream"
+    torch.cuda.set_stream(stream)
+    capi.check(L.psm_set_stream(de.handle, C.c_void_p(stream.cuda_stream)), de.handle)
+
+    npix = W * H
+    lmap = torch.empty((H, W), dtype=torch.uint8).pin_memory()
+    rmap = torch.empty((H, W), dtype=torch.uint8).pin_memory()
+    if world > 1:
+        keys = torch.empty((2, npix), dtype=torch.int64, device="cuda")
+        gathered = torch.empty((2, world, npix), dtype=torch.int64, device="cuda")
+    step_bytes = W * 3 * 4
+
+    def step(e2e):
+        if e2e:
+            capi.check(L.psm_set_images(de.handle, lp.data_ptr(), step_bytes, rp.data_ptr(), step_bytes), de.handle)
+        else:
+            capi.check(L.psm_set_images_device(de.handle, ld_dev.data_ptr(), step_bytes, rd_dev.data_ptr(), step_bytes), de.handle)
+        capi.check(L.psm_cost_const(de.handle), de.handle)
+        capi.check(L.psm_cost_filter(de.handle), de.handle)
+        if world == 1:
+            if e2e:
+                capi.check(L.psm_disp_select(de.handle, lmap.data_ptr(), W, rmap.data_ptr(), W), de.handle)
+            else:
+                capi.check(L.psm_disp_select_device(de.handle), de.handle)
+        else:
+            capi.check(L.psm_disp_select_keys(de.handle, keys[0].data_ptr(), keys[1].data_ptr()), de.handle)
+            dist.all_gather_into_tensor(gathered[0].view(-1), keys[0])
+            dist.all_gather_into_tensor(gathered[1].view(-1), keys[1])
+            out_l = lmap.data_ptr() if e2e else None
+            out_r = rmap.data_ptr() if e2e else None
+            capi.check(L.psm_disp_reduce_keys(de.handle, gathered[0].data_ptr(), gathered[1].data_ptr(), world,
+                                              out_l, W, out_r, W), de.handle)
+
+    def timed(e2e, steps, collect_kernel=False):
+        for _ in range(warm):
+            step(e2e)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kms = []
+        e0.record(stream)
+        for _ in range(steps):
+            step(e2e)
+            if collect_kernel:
+                kms.append(de.stage_ms(4))  # the fused CVF kernel alone, cudaEvents on the launching stream
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), kms
+
+    launches0 = de.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms, kms = timed(False, args.steps, collect_kernel=True)
+    clocks = sampler.stop() if rank == 0 else None
+    launches_per_step = (de.launch_count() - launches0) // (warm + args.steps)
+    stage = {n: de.stage_ms(i) for i, n in enumerate(["ingest", "cvc", "cvf", "wta", "cvf_kernel"])}
+    e2e_ms, _ = timed(True, args.steps)
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = 1e3 / ms_per_step
+        e2e_value = 1e3 / (e2e_ms / args.steps)
+        peak, peak_src = measured_peaks()
+        V = W * H * d_count
+        algo_bytes = 2 * (8 * V + 48 * W * H)  # one launch filters both views: read p + write q + 12 guide floats/px
+        kern_ms = float(np.mean(kms))
+        achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "cvf_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": f"disparity-sharded x{world}" if world > 1 else "single GPU",
+                       "cvf_mode": ["exact", "mixed", "naive"][args.cvf_mode], "variant": args.variant,
+                       "l2": "inputs larger than L2: each step streams 4 x 1.06 GB volumes (raw+filtered, 2 views), no flush needed",
+                       "stage_ms_last_step": stage},
+            "roofline": {"bound": "hbm", "kernel": "cvf_stream_kernel (fused guided filter, both views per launch)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_ms,
+                         "peak_source": peak_src},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * W * H * 3 * 4 * world,
+                    "d2h_bytes_per_step": 2 * W * H * world, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            threads = min(cores, D)
+            sec, tms = oracle_frame(l, r, threads)
+            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "1 full C4 frame (both views) through the CPU oracle, all host cores",
+                                    "stage_ms": {"cvc": tms[0], "cvf": tms[1], "wta": tms[2]}}
+        print(json.dumps(line), flush=True)
+    de.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,162 @@
+/*
+ * prime_stereo_b200.h -- C-ABI of the B200-native STEREO_GIF hot path
+ * (cost-volume construction -> guided-image-filter cost aggregation -> WTA).
+ *
+ * This is the drop-in boundary that sits under the reference's DispEst "_GPU" stage
+ * methods (the `m`-toggle compute mode).  Plain C linkage, plain pointers and sizes,
+ * no C++/torch/OpenCV types.  Every entry point returns 0 on success and a non-zero
+ * PSM_E* code on failure (the reference's stage methods are `int`, 0 = success:
+ * /root/reference/src/DispEst.cpp:275,307,327); psm_last_error() gives the text.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   psm_device_count      <-> openCLdevicepoll()                 src/main.cpp:29, src/oclUtil.cpp:18
+ *   psm_create / destroy  <-> DispEst::DispEst(..., ocl=true) OpenCL part / ~DispEst
+ *                                                                 src/DispEst.cpp:57-140, :145-162
+ *   psm_set_images        <-> DispEst::setInputImages + H2D in CVC_cl::buildCV
+ *                                                                 src/DispEst.cpp:164-170, src/CVC_cl.cpp:93-160
+ *   psm_cost_const        <-> DispEst::CostConst_GPU             src/DispEst.cpp:272-276
+ *   psm_cost_filter       <-> DispEst::CostFilter_GPU            src/DispEst.cpp:299-308
+ *   psm_disp_select       <-> DispEst::DispSelect_GPU + D2H in DispSel_cl::CVSelect
+ *                                                                 src/DispEst.cpp:323-328, src/DispSel_cl.cpp:123-134
+ *   psm_read_cost_slice   <-> DispEst::printCV (cost-slice dump) src/DispEst.cpp:181-194
+ *   psm_stage_ms          <-> cvc_time/cvf_time/dispsel_time     src/StereoMatch.cpp:209-241
+ *
+ * Numerics contract: results equal the reference's pthreads CPU path
+ * (src/CVC.cpp, src/CVF.cpp, src/DispSel.cpp), NOT the divergent OpenCL kernels
+ * (SURVEY.md section 2.1).  See DESIGN.md.
+ *
+ * Threading: one psm_ctx must not be used concurrently; it may be used from different
+ * host threads over its life (every call binds its CUDA device first), matching how the
+ * reference constructs DispEst on the HCI thread and runs stages on the worker thread.
+ */
+#ifndef PRIME_STEREO_B200_H
+#define PRIME_STEREO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct psm_ctx psm_ctx;
+
+enum {
+    PSM_OK = 0,
+    PSM_EINVAL = 1,   /* bad argument */
+    PSM_ECUDA = 2,    /* CUDA runtime error (text in psm_last_error) */
+    PSM_ESTATE = 3,   /* stage called out of order (images not set, ...) */
+    PSM_ENOMEM = 4
+};
+
+/* Views */
+enum { PSM_LEFT = 0, PSM_RIGHT = 1 };
+
+/* psm_set_option keys */
+enum {
+    PSM_OPT_CVF_MODE = 1,  /* PSM_CVF_* below; default PSM_CVF_EXACT */
+    PSM_OPT_GRAY_MODE = 2, /* 0: fma(c2,.114,fma(c0,.299,c1*.587)) (OpenCV SIMD/IPP builds, default)
+                              1: (c0*.299+c1*.587)+c2*.114 (non-FMA OpenCV builds) */
+    PSM_OPT_TIMING = 3     /* 1: record cudaEvents around each stage (default 1) */
+};
+enum {
+    PSM_CVF_EXACT = 0, /* streaming fused kernel, every box sum accumulated in fp64: bit-exact q */
+    PSM_CVF_MIXED = 1, /* stage-1 boxes fp64 (a,b bit-exact), stage-2 boxes fp32: |dq| ~1e-6 */
+    PSM_CVF_NAIVE = 2  /* unfused two-pass direct 64-tap fp64 kernels: slow device-side cross-check */
+};
+
+/* Number of usable CUDA devices (0 if none / no driver): gates the `m` toggle. */
+int psm_device_count(void);
+
+/* Create a context for W x H images and disparities [0, max_disp) on CUDA device `device`.
+ * Allocates all device state (planar images, gradients, guide planes, both cost volumes,
+ * disparity maps).  max_disp <= 256 (u8 disparity maps). */
+int psm_create(psm_ctx** out, int width, int height, int max_disp, int device);
+
+/* Disparity-sharded context (multi-GPU, one context per GPU): this context owns the global
+ * slices [d_begin, d_begin + d_count) of a max_disp-deep problem.  psm_create == shard [0,max_disp). */
+int psm_create_sharded(psm_ctx** out, int width, int height, int max_disp,
+                       int d_begin, int d_count, int device);
+
+int psm_destroy(psm_ctx* ctx);
+
+int psm_set_option(psm_ctx* ctx, int key, int value);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*) for all work; NULL restores the
+ * context's own stream.  Lets a caller time with its own events on that stream. */
+int psm_set_stream(psm_ctx* ctx, void* cuda_stream);
+
+/* Inputs: interleaved 3-channel float images (cv::Mat CV_32FC3, BGR, values in [0,1]) in HOST
+ * memory, row steps in BYTES.  Copies H2D and builds planar channels + x-gradients
+ * (CVC::preprocess, src/CVC.cpp:41-46) on the device. */
+int psm_set_images(psm_ctx* ctx, const float* left, size_t left_step,
+                   const float* right, size_t right_step);
+
+/* Same, 8-bit interleaved BGR input; the convertTo(CV_32F, 1/255.0f) of
+ * src/StereoMatch.cpp:193-197 is done on the device (4x less H2D traffic). */
+int psm_set_images_u8(psm_ctx* ctx, const uint8_t* left, size_t left_step,
+                      const uint8_t* right, size_t right_step);
+
+/* Same as psm_set_images but the interleaved float images already live in DEVICE memory. */
+int psm_set_images_device(psm_ctx* ctx, const float* d_left, size_t left_step,
+                          const float* d_right, size_t right_step);
+
+/* Stage 1: both raw cost volumes (CostConst_GPU). Asynchronous on the context stream. */
+int psm_cost_const(psm_ctx* ctx);
+
+/* Stage 2: guide precompute + guided filter of every slice of both volumes, in place
+ * (CostFilter_GPU). Asynchronous on the context stream. */
+int psm_cost_filter(psm_ctx* ctx);
+
+/* Stage 3: WTA over d in [1, max_disp) for both views; copies the u8 maps to HOST memory
+ * (row steps in bytes) and synchronises (DispSelect_GPU).  Only valid on an unsharded context. */
+int psm_disp_select(psm_ctx* ctx, uint8_t* left, size_t left_step,
+                    uint8_t* right, size_t right_step);
+
+/* Stage 3 without the D2H copy: maps stay on the device (see psm_device_ptr). Asynchronous. */
+int psm_disp_select_device(psm_ctx* ctx);
+
+/* Sharded stage 3a: per-pixel packed minima over this context's slices, written to DEVICE
+ * buffers of H*W uint64 each:  key = (order_preserving_u32(cost) << 32) | global_d.
+ * min() over ranks' keys reproduces the reference's strict-< / lowest-d tie-break. Asynchronous. */
+int psm_disp_select_keys(psm_ctx* ctx, uint64_t* d_keys_left, uint64_t* d_keys_right);
+
+/* Sharded stage 3b: reduce `nranks` gathered key planes (DEVICE, [nranks][H*W] per view) to the
+ * final u8 maps in HOST memory and synchronise. */
+int psm_disp_reduce_keys(psm_ctx* ctx, const uint64_t* d_gathered_left,
+                         const uint64_t* d_gathered_right, int nranks,
+                         uint8_t* left, size_t left_step, uint8_t* right, size_t right_step);
+
+/* Debug / parity reads (synchronising). `d` is a GLOBAL disparity index owned by this context. */
+int psm_read_cost_slice(psm_ctx* ctx, int view, int d, float* dst, size_t dst_step);
+int psm_write_cost_slice(psm_ctx* ctx, int view, int d, const float* src, size_t src_step);
+/* plane ids: 0-2 I (split channels), 3-5 mean_I, 6-11 var_I (rr,rg,rb,gg,gb,bb), 12 x-gradient */
+int psm_read_guide_plane(psm_ctx* ctx, int view, int plane, float* dst, size_t dst_step);
+/* guided-filter coefficients of one raw slice (a0,a1,a2,b; each H*W floats, dense rows), computed
+ * from the CURRENT content of slice d (call between psm_cost_const and psm_cost_filter). */
+int psm_read_ab_slice(psm_ctx* ctx, int view, int d, float* a3, float* b);
+
+/* Device pointers for zero-copy callers / benchmarks. what: 0 left volume, 1 right volume,
+ * 2 left u8 map, 3 right u8 map.  pitch_elems receives the row pitch in elements. */
+int psm_device_ptr(psm_ctx* ctx, int what, void** ptr, size_t* pitch_elems);
+
+/* Last measured stage durations in milliseconds (cudaEvent pairs on the context stream):
+ * stage 0 ingest (H2D + planar/gradient), 1 CVC, 2 CVF (guide + filter), 3 WTA, 4 CVF filter kernel only.
+ * Synchronises on the stage's end event. */
+int psm_stage_ms(psm_ctx* ctx, int stage, float* ms);
+
+/* Number of kernels this context launched since creation (bench.py "gpu_launches"). */
+int psm_launch_count(psm_ctx* ctx, uint64_t* n);
+
+int psm_sync(psm_ctx* ctx);
+
+/* Human-readable text of the last error on this context (or the last creation error if ctx==NULL). */
+const char* psm_last_error(psm_ctx* ctx);
+
+/* Library build info string: version, arch, compile flags. */
+const char* psm_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRIME_STEREO_B200_H */

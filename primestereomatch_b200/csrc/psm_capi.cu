@@ -1,0 +1,567 @@
+// psm_capi.cu -- the C-ABI (include/prime_stereo_b200.h) over the sm_100a kernels.
+// Host logic only: context/buffer ownership, stage ordering, launches, timers.  No CPU
+// compute path exists here: every stage is a CUDA kernel launch or it fails.
+#include "../../include/prime_stereo_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "psm_cvf_stream.cuh"
+
+#ifndef PSM_BUILD_FLAGS
+#define PSM_BUILD_FLAGS "unknown"
+#endif
+
+using namespace psm;
+
+namespace {
+
+constexpr int kNumStages = 5;  // ingest, cvc, cvf, wta, cvf-filter-kernel
+
+char g_create_error[512] = "";
+
+}  // namespace
+
+struct psm_ctx {
+    int W = 0, H = 0, Wp = 0, D = 0, d_begin = 0, d_count = 0, device = 0;
+    size_t plane = 0;  // H * Wp
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    float* guide[2] = {nullptr, nullptr};   // kGuidePlanes planes per view
+    float* grd[2] = {nullptr, nullptr};
+    float* vol[2] = {nullptr, nullptr};     // current volumes (raw after CVC, filtered after CVF)
+    float* vol_alt[2] = {nullptr, nullptr}; // the other half of the ping-pong
+    double* hs = nullptr;                   // guide precompute scratch [9][H][W] fp64
+    void* stage_in[2] = {nullptr, nullptr}; // device staging for the interleaved upload
+    uint8_t* dis[2] = {nullptr, nullptr};
+    float* ab = nullptr;                    // naive-mode scratch [4][d_count][H][Wp], lazy
+    size_t ab_slices = 0;
+    cudaEvent_t ev0[kNumStages] = {}, ev1[kNumStages] = {};
+    bool ev_valid[kNumStages] = {};
+    int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0;
+    bool have_images = false, guide_valid = false, have_cvc = false;
+    uint64_t launches = 0;
+    char err[512] = "";
+};
+
+namespace {
+
+int fail(psm_ctx* c, int code, const char* fmt, ...)
+{
+    char* dst = c ? c->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define PSM_CUDA(c, call)                                                                          \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail((c), PSM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),   \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+#define PSM_LAUNCH_CHECK(c)                                                                        \
+    do {                                                                                           \
+        (c)->launches++;                                                                           \
+        PSM_CUDA((c), cudaGetLastError());                                                         \
+    } while (0)
+
+int bind(psm_ctx* c)
+{
+    if (!c) return fail(nullptr, PSM_EINVAL, "null context");
+    PSM_CUDA(c, cudaSetDevice(c->device));
+    return PSM_OK;
+}
+
+int stage_begin(psm_ctx* c, int s)
+{
+    if (c->timing) PSM_CUDA(c, cudaEventRecord(c->ev0[s], c->stream));
+    return PSM_OK;
+}
+int stage_end(psm_ctx* c, int s)
+{
+    if (c->timing) { PSM_CUDA(c, cudaEventRecord(c->ev1[s], c->stream)); c->ev_valid[s] = true; }
+    return PSM_OK;
+}
+
+template <typename T>
+int ingest(psm_ctx* c, const T* l, size_t lstep, const T* r, size_t rstep, bool from_device)
+{
+    const T* src[2] = {l, r};
+    const size_t step[2] = {lstep, rstep};
+    const size_t row_bytes = (size_t)c->W * 3 * sizeof(T);
+    for (int v = 0; v < 2; ++v) {
+        if (!src[v] || step[v] < row_bytes) return fail(c, PSM_EINVAL, "bad image pointer/step for view %d", v);
+        const T* dsrc = src[v];
+        size_t dstep = step[v];
+        if (!from_device) {
+            PSM_CUDA(c, cudaMemcpy2DAsync(c->stage_in[v], row_bytes, src[v], step[v], row_bytes, c->H,
+                                          cudaMemcpyHostToDevice, c->stream));
+            dsrc = static_cast<const T*>(c->stage_in[v]);
+            dstep = row_bytes;
+        }
+        float* g = c->guide[v];
+        dim3 blk(128), grd((c->Wp + 127) / 128, c->H);
+        ingest_kernel<T><<<grd, blk, 0, c->stream>>>(dsrc, dstep, c->W, c->H, c->Wp, g, g + c->plane,
+                                                      g + 2 * c->plane, c->grd[v], c->gray_mode);
+        PSM_LAUNCH_CHECK(c);
+    }
+    c->have_images = true;
+    c->guide_valid = false;
+    c->have_cvc = false;
+    return PSM_OK;
+}
+
+int ensure_guide(psm_ctx* c)
+{
+    if (c->guide_valid) return PSM_OK;
+    for (int v = 0; v < 2; ++v) {
+        dim3 blk(128), g1((c->W + 127) / 128, c->H), g2((c->Wp + 127) / 128, c->H);
+        guide_hsum_kernel<<<g1, blk, 0, c->stream>>>(c->guide[v], c->plane, c->W, c->H, c->Wp, c->hs);
+        PSM_LAUNCH_CHECK(c);
+        guide_finish_kernel<<<g2, blk, 0, c->stream>>>(c->hs, c->guide[v], c->plane, c->W, c->H, c->Wp);
+        PSM_LAUNCH_CHECK(c);
+    }
+    c->guide_valid = true;
+    return PSM_OK;
+}
+
+int ensure_ab(psm_ctx* c, size_t slices)
+{
+    if (c->ab && c->ab_slices >= slices) return PSM_OK;
+    if (c->ab) { cudaFree(c->ab); c->ab = nullptr; c->ab_slices = 0; }
+    PSM_CUDA(c, cudaMalloc(&c->ab, 4 * slices * c->plane * sizeof(float)));
+    c->ab_slices = slices;
+    return PSM_OK;
+}
+
+// Row segmentation of the streaming kernel: segments are multiples of 8 rows, >= 16 rows, and the
+// last one keeps >= 8 rows so that only the first/last segment ever sees a reflected row.
+void plan_segments(int H, int target_rows, int* nseg, int* seg_rows)
+{
+    int n = H / target_rows;
+    if (n < 1) n = 1;
+    for (; n > 1; --n) {
+        int rows = (H + n - 1) / n;
+        rows = (rows + 7) & ~7;
+        if (rows < 16) continue;
+        const int last = H - (n - 1) * rows;
+        if (last >= 8) { *nseg = n; *seg_rows = rows; return; }
+    }
+    *nseg = 1;
+    *seg_rows = (H + 7) & ~7;
+}
+
+template <int DT, int NW>
+int launch_cvf_stream(psm_ctx* c)
+{
+    CvfParams P;
+    for (int v = 0; v < 2; ++v) { P.vol_in[v] = c->vol[v]; P.vol_out[v] = c->vol_alt[v]; P.guide[v] = c->guide[v]; }
+    P.W = c->W; P.H = c->H; P.Wp = c->Wp; P.Dloc = c->d_count;
+    P.nstrips = (c->W + kStripOut - 1) / kStripOut;
+    P.ndgroups = (c->d_count + DT * NW - 1) / (DT * NW);
+    // enough CTAs for several waves over 148 SMs, but segments no shorter than ~128 rows (each
+    // segment pays ~11 warm-up rows)
+    int target_rows = 256;
+    const long ctas_1seg = 2L * P.nstrips * P.ndgroups;
+    if (ctas_1seg * (c->H / 256 > 0 ? c->H / 256 : 1) < 148 * 3 * 4) target_rows = 128;
+    plan_segments(c->H, target_rows, &P.nseg, &P.seg_rows);
+    const size_t smem = (size_t)8 * 4 * DT * NW * 32 * sizeof(float4);
+    auto kern = cvf_stream_kernel<DT, NW>;
+    PSM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = 2u * P.nseg * P.nstrips * P.ndgroups;
+    kern<<<grid, NW * 32, smem, c->stream>>>(P);
+    PSM_LAUNCH_CHECK(c);
+    return PSM_OK;
+}
+
+int copy_map_out(psm_ctx* c, const uint8_t* dsrc, uint8_t* dst, size_t step)
+{
+    if (!dst || step < (size_t)c->W) return fail(c, PSM_EINVAL, "bad disparity map pointer/step");
+    PSM_CUDA(c, cudaMemcpy2DAsync(dst, step, dsrc, c->W, c->W, c->H, cudaMemcpyDeviceToHost, c->stream));
+    return PSM_OK;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int psm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* psm_build_info(void)
+{
+    return "prime_stereo_b200 0.1 (sm_100a; " PSM_BUILD_FLAGS ")";
+}
+
+const char* psm_last_error(psm_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+int psm_create_sharded(psm_ctx** out, int width, int height, int max_disp, int d_begin, int d_count, int device)
+{
+    if (!out) return fail(nullptr, PSM_EINVAL, "out is null");
+    *out = nullptr;
+    if (width < 1 || height < 1 || max_disp < 2 || max_disp > 256)
+        return fail(nullptr, PSM_EINVAL, "bad geometry W=%d H=%d D=%d (need W,H>=1, 2<=D<=256)", width, height, max_disp);
+    if (d_begin < 0 || d_count < 1 || d_begin + d_count > max_disp)
+        return fail(nullptr, PSM_EINVAL, "bad shard [%d,%d) of %d", d_begin, d_begin + d_count, max_disp);
+    int ndev = psm_device_count();
+    if (device < 0 || device >= ndev) return fail(nullptr, PSM_ECUDA, "CUDA device %d not available (%d devices)", device, ndev);
+    psm_ctx* c = new (std::nothrow) psm_ctx();
+    if (!c) return fail(nullptr, PSM_ENOMEM, "out of host memory");
+    c->W = width; c->H = height; c->Wp = (width + 3) & ~3; c->D = max_disp;
+    c->d_begin = d_begin; c->d_count = d_count; c->device = device;
+    c->plane = (size_t)c->H * c->Wp;
+    auto bail = [&](int code) {
+        snprintf(g_create_error, sizeof(g_create_error), "%s", c->err);
+        psm_destroy(c);
+        return code;
+    };
+#define PSM_CREATE_CUDA(call)                                                                    \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            fail(c, PSM_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e__));                 \
+            return bail(e__ == cudaErrorMemoryAllocation ? PSM_ENOMEM : PSM_ECUDA);              \
+        }                                                                                        \
+    } while (0)
+    PSM_CREATE_CUDA(cudaSetDevice(device));
+    PSM_CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    const size_t vol_bytes = (size_t)d_count * c->plane * sizeof(float);
+    for (int v = 0; v < 2; ++v) {
+        PSM_CREATE_CUDA(cudaMalloc(&c->guide[v], kGuidePlanes * c->plane * sizeof(float)));
+        PSM_CREATE_CUDA(cudaMalloc(&c->grd[v], c->plane * sizeof(float)));
+        PSM_CREATE_CUDA(cudaMalloc(&c->vol[v], vol_bytes));
+        PSM_CREATE_CUDA(cudaMalloc(&c->vol_alt[v], vol_bytes));
+        PSM_CREATE_CUDA(cudaMalloc(&c->stage_in[v], (size_t)c->W * c->H * 3 * sizeof(float)));
+        PSM_CREATE_CUDA(cudaMalloc(&c->dis[v], (size_t)c->W * c->H));
+        PSM_CREATE_CUDA(cudaMemsetAsync(c->vol[v], 0, vol_bytes, c->stream));  // DispEst.cpp:31-37 zero-init
+        PSM_CREATE_CUDA(cudaMemsetAsync(c->vol_alt[v], 0, vol_bytes, c->stream));
+        PSM_CREATE_CUDA(cudaMemsetAsync(c->dis[v], 0, (size_t)c->W * c->H, c->stream));
+    }
+    PSM_CREATE_CUDA(cudaMalloc(&c->hs, (size_t)9 * c->W * c->H * sizeof(double)));
+    for (int s = 0; s < kNumStages; ++s) {
+        PSM_CREATE_CUDA(cudaEventCreate(&c->ev0[s]));
+        PSM_CREATE_CUDA(cudaEventCreate(&c->ev1[s]));
+    }
+    PSM_CREATE_CUDA(cudaStreamSynchronize(c->stream));
+#undef PSM_CREATE_CUDA
+    *out = c;
+    return PSM_OK;
+}
+
+int psm_create(psm_ctx** out, int width, int height, int max_disp, int device)
+{
+    return psm_create_sharded(out, width, height, max_disp, 0, max_disp, device);
+}
+
+int psm_destroy(psm_ctx* c)
+{
+    if (!c) return PSM_OK;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    for (int v = 0; v < 2; ++v) {
+        cudaFree(c->guide[v]); cudaFree(c->grd[v]); cudaFree(c->vol[v]); cudaFree(c->vol_alt[v]);
+        cudaFree(c->stage_in[v]); cudaFree(c->dis[v]);
+    }
+    cudaFree(c->hs);
+    cudaFree(c->ab);
+    for (int s = 0; s < kNumStages; ++s) {
+        if (c->ev0[s]) cudaEventDestroy(c->ev0[s]);
+        if (c->ev1[s]) cudaEventDestroy(c->ev1[s]);
+    }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    cudaGetLastError();
+    delete c;
+    return PSM_OK;
+}
+
+int psm_set_option(psm_ctx* c, int key, int value)
+{
+    if (!c) return fail(nullptr, PSM_EINVAL, "null context");
+    switch (key) {
+    case PSM_OPT_CVF_MODE:
+        if (value != PSM_CVF_EXACT && value != PSM_CVF_MIXED && value != PSM_CVF_NAIVE)
+            return fail(c, PSM_EINVAL, "unknown CVF mode %d", value);
+        if (value == PSM_CVF_MIXED) return fail(c, PSM_EINVAL, "PSM_CVF_MIXED is not built in this version");
+        c->cvf_mode = value;
+        return PSM_OK;
+    case PSM_OPT_GRAY_MODE:
+        if (value != 0 && value != 1) return fail(c, PSM_EINVAL, "gray mode must be 0 or 1");
+        c->gray_mode = value;
+        return PSM_OK;
+    case PSM_OPT_TIMING:
+        c->timing = value ? 1 : 0;
+        return PSM_OK;
+    case 100:  // undocumented: streaming-kernel variant selector for tuning experiments
+        c->cvf_variant = value;
+        return PSM_OK;
+    default:
+        return fail(c, PSM_EINVAL, "unknown option %d", key);
+    }
+}
+
+int psm_set_stream(psm_ctx* c, void* cuda_stream)
+{
+    if (int rc = bind(c)) return rc;
+    PSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return PSM_OK;
+}
+
+int psm_set_images(psm_ctx* c, const float* left, size_t left_step, const float* right, size_t right_step)
+{
+    if (int rc = bind(c)) return rc;
+    if (int rc = stage_begin(c, 0)) return rc;
+    if (int rc = ingest<float>(c, left, left_step, right, right_step, false)) return rc;
+    return stage_end(c, 0);
+}
+
+int psm_set_images_u8(psm_ctx* c, const uint8_t* left, size_t left_step, const uint8_t* right, size_t right_step)
+{
+    if (int rc = bind(c)) return rc;
+    if (int rc = stage_begin(c, 0)) return rc;
+    if (int rc = ingest<uint8_t>(c, left, left_step, right, right_step, false)) return rc;
+    return stage_end(c, 0);
+}
+
+int psm_set_images_device(psm_ctx* c, const float* d_left, size_t left_step, const float* d_right, size_t right_step)
+{
+    if (int rc = bind(c)) return rc;
+    if (int rc = stage_begin(c, 0)) return rc;
+    if (int rc = ingest<float>(c, d_left, left_step, d_right, right_step, true)) return rc;
+    return stage_end(c, 0);
+}
+
+int psm_cost_const(psm_ctx* c)
+{
+    if (int rc = bind(c)) return rc;
+    if (!c->have_images) return fail(c, PSM_ESTATE, "psm_cost_const before psm_set_images");
+    if (int rc = stage_begin(c, 1)) return rc;
+    for (int v = 0; v < 2; ++v) {
+        CvcParams P;
+        const float* gs = c->guide[v];
+        const float* go = c->guide[1 - v];
+        for (int k = 0; k < 3; ++k) { P.self[k] = gs + k * c->plane; P.other[k] = go + k * c->plane; }
+        P.self[3] = c->grd[v];
+        P.other[3] = c->grd[1 - v];
+        P.vol = c->vol[v];
+        P.W = c->W; P.H = c->H; P.Wp = c->Wp; P.d_begin = c->d_begin; P.d_count = c->d_count;
+        dim3 blk(128), grd((c->Wp / 4 + 127) / 128, c->H);
+        if (v == PSM_LEFT) cvc_kernel<-1><<<grd, blk, 0, c->stream>>>(P);
+        else cvc_kernel<+1><<<grd, blk, 0, c->stream>>>(P);
+        PSM_LAUNCH_CHECK(c);
+    }
+    c->have_cvc = true;
+    return stage_end(c, 1);
+}
+
+int psm_cost_filter(psm_ctx* c)
+{
+    if (int rc = bind(c)) return rc;
+    if (!c->have_cvc) return fail(c, PSM_ESTATE, "psm_cost_filter before psm_cost_const");
+    if (int rc = stage_begin(c, 2)) return rc;
+    if (int rc = ensure_guide(c)) return rc;
+    const bool tiny = c->W < 16 || c->H < 16;
+    if (c->cvf_mode == PSM_CVF_NAIVE || tiny) {
+        if (int rc = ensure_ab(c, (size_t)c->d_count)) return rc;
+        if (int rc = stage_begin(c, 4)) return rc;
+        for (int v = 0; v < 2; ++v) {
+            dim3 blk(128), grd((c->W + 127) / 128, c->H, c->d_count);
+            cvf_naive_ab_kernel<<<grd, blk, 0, c->stream>>>(c->vol[v], c->guide[v], c->plane, c->W, c->H, c->Wp,
+                                                          c->d_count, c->ab);
+            PSM_LAUNCH_CHECK(c);
+            cvf_naive_q_kernel<<<grd, blk, 0, c->stream>>>(c->ab, c->guide[v], c->plane, c->W, c->H, c->Wp,
+                                                         c->d_count, c->vol_alt[v]);
+            PSM_LAUNCH_CHECK(c);
+        }
+        if (int rc = stage_end(c, 4)) return rc;
+    } else {
+        if (int rc = stage_begin(c, 4)) return rc;
+        int rc = (c->cvf_variant == 1) ? launch_cvf_stream<2, 2>(c) : launch_cvf_stream<1, 4>(c);
+        if (rc) return rc;
+        if (int rc2 = stage_end(c, 4)) return rc2;
+    }
+    for (int v = 0; v < 2; ++v) { float* t = c->vol[v]; c->vol[v] = c->vol_alt[v]; c->vol_alt[v] = t; }
+    c->have_cvc = false;  // the volumes now hold filtered costs; filtering again needs a new CVC
+    return stage_end(c, 2);
+}
+
+int psm_disp_select_device(psm_ctx* c)
+{
+    if (int rc = bind(c)) return rc;
+    if (c->d_begin != 0 || c->d_count != c->D)
+        return fail(c, PSM_ESTATE, "psm_disp_select on a sharded context: use psm_disp_select_keys + psm_disp_reduce_keys");
+    if (int rc = stage_begin(c, 3)) return rc;
+    for (int v = 0; v < 2; ++v) {
+        dim3 blk(256), grd(((c->W + 3) / 4 + 255) / 256, c->H);
+        wta_kernel<<<grd, blk, 0, c->stream>>>(c->vol[v], c->W, c->H, c->Wp, c->d_begin, c->d_count, c->dis[v], nullptr);
+        PSM_LAUNCH_CHECK(c);
+    }
+    return stage_end(c, 3);
+}
+
+int psm_disp_select(psm_ctx* c, uint8_t* left, size_t left_step, uint8_t* right, size_t right_step)
+{
+    if (int rc = psm_disp_select_device(c)) return rc;
+    if (int rc = copy_map_out(c, c->dis[0], left, left_step)) return rc;
+    if (int rc = copy_map_out(c, c->dis[1], right, right_step)) return rc;
+    PSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PSM_OK;
+}
+
+int psm_disp_select_keys(psm_ctx* c, uint64_t* d_keys_left, uint64_t* d_keys_right)
+{
+    if (int rc = bind(c)) return rc;
+    if (!d_keys_left || !d_keys_right) return fail(c, PSM_EINVAL, "null key buffer");
+    if (int rc = stage_begin(c, 3)) return rc;
+    uint64_t* keys[2] = {d_keys_left, d_keys_right};
+    for (int v = 0; v < 2; ++v) {
+        dim3 blk(256), grd(((c->W + 3) / 4 + 255) / 256, c->H);
+        wta_kernel<<<grd, blk, 0, c->stream>>>(c->vol[v], c->W, c->H, c->Wp, c->d_begin, c->d_count, nullptr,
+                                               reinterpret_cast<unsigned long long*>(keys[v]));
+        PSM_LAUNCH_CHECK(c);
+    }
+    return stage_end(c, 3);
+}
+
+int psm_disp_reduce_keys(psm_ctx* c, const uint64_t* d_gathered_left, const uint64_t* d_gathered_right, int nranks,
+                         uint8_t* left, size_t left_step, uint8_t* right, size_t right_step)
+{
+    if (int rc = bind(c)) return rc;
+    if (!d_gathered_left || !d_gathered_right || nranks < 1) return fail(c, PSM_EINVAL, "bad gathered keys");
+    const uint64_t* g[2] = {d_gathered_left, d_gathered_right};
+    const size_t npix = (size_t)c->W * c->H;
+    for (int v = 0; v < 2; ++v) {
+        keys_reduce_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, c->stream>>>(
+            reinterpret_cast<const unsigned long long*>(g[v]), nranks, npix, c->dis[v]);
+        PSM_LAUNCH_CHECK(c);
+    }
+    if (left && right) {
+        if (int rc = copy_map_out(c, c->dis[0], left, left_step)) return rc;
+        if (int rc = copy_map_out(c, c->dis[1], right, right_step)) return rc;
+    }
+    PSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PSM_OK;
+}
+
+static int check_slice(psm_ctx* c, int view, int d)
+{
+    if (view != PSM_LEFT && view != PSM_RIGHT) return fail(c, PSM_EINVAL, "bad view %d", view);
+    if (d < c->d_begin || d >= c->d_begin + c->d_count)
+        return fail(c, PSM_EINVAL, "slice %d not owned by this context [%d,%d)", d, c->d_begin, c->d_begin + c->d_count);
+    return PSM_OK;
+}
+
+int psm_read_cost_slice(psm_ctx* c, int view, int d, float* dst, size_t dst_step)
+{
+    if (int rc = bind(c)) return rc;
+    if (int rc = check_slice(c, view, d)) return rc;
+    if (!dst || dst_step < (size_t)c->W * sizeof(float)) return fail(c, PSM_EINVAL, "bad dst/step");
+    PSM_CUDA(c, cudaMemcpy2DAsync(dst, dst_step, c->vol[view] + (size_t)(d - c->d_begin) * c->plane,
+                                  c->Wp * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyDeviceToHost, c->stream));
+    PSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PSM_OK;
+}
+
+int psm_write_cost_slice(psm_ctx* c, int view, int d, const float* src, size_t src_step)
+{
+    if (int rc = bind(c)) return rc;
+    if (int rc = check_slice(c, view, d)) return rc;
+    if (!src || src_step < (size_t)c->W * sizeof(float)) return fail(c, PSM_EINVAL, "bad src/step");
+    PSM_CUDA(c, cudaMemcpy2DAsync(c->vol[view] + (size_t)(d - c->d_begin) * c->plane, c->Wp * sizeof(float), src,
+                                  src_step, c->W * sizeof(float), c->H, cudaMemcpyHostToDevice, c->stream));
+    PSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->have_cvc = true;  // caller-provided raw costs may be filtered
+    return PSM_OK;
+}
+
+int psm_read_guide_plane(psm_ctx* c, int view, int plane_id, float* dst, size_t dst_step)
+{
+    if (int rc = bind(c)) return rc;
+    if (view != PSM_LEFT && view != PSM_RIGHT) return fail(c, PSM_EINVAL, "bad view %d", view);
+    if (!c->have_images) return fail(c, PSM_ESTATE, "no images set");
+    if (!dst || dst_step < (size_t)c->W * sizeof(float)) return fail(c, PSM_EINVAL, "bad dst/step");
+    const float* src = nullptr;
+    if (plane_id >= 0 && plane_id <= 2) src = c->guide[view] + (size_t)plane_id * c->plane;
+    else if (plane_id >= 3 && plane_id <= 5) src = c->guide[view] + (size_t)(kGuideMean + plane_id - 3) * c->plane;
+    else if (plane_id >= 6 && plane_id <= 11) src = c->guide[view] + (size_t)(kGuideVar + plane_id - 6) * c->plane;
+    else if (plane_id == 12) src = c->grd[view];
+    else return fail(c, PSM_EINVAL, "bad plane id %d", plane_id);
+    if (plane_id >= 3 && plane_id <= 11)
+        if (int rc = ensure_guide(c)) return rc;
+    PSM_CUDA(c, cudaMemcpy2DAsync(dst, dst_step, src, c->Wp * sizeof(float), c->W * sizeof(float), c->H,
+                                  cudaMemcpyDeviceToHost, c->stream));
+    PSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PSM_OK;
+}
+
+int psm_read_ab_slice(psm_ctx* c, int view, int d, float* a3, float* b)
+{
+    if (int rc = bind(c)) return rc;
+    if (int rc = check_slice(c, view, d)) return rc;
+    if (!a3 || !b) return fail(c, PSM_EINVAL, "null output");
+    if (!c->have_images) return fail(c, PSM_ESTATE, "no images set");
+    if (int rc = ensure_guide(c)) return rc;
+    if (int rc = ensure_ab(c, 1)) return rc;
+    dim3 blk(128), grd((c->W + 127) / 128, c->H, 1);
+    cvf_naive_ab_kernel<<<grd, blk, 0, c->stream>>>(c->vol[view] + (size_t)(d - c->d_begin) * c->plane, c->guide[view],
+                                                  c->plane, c->W, c->H, c->Wp, 1, c->ab);
+    PSM_LAUNCH_CHECK(c);
+    const size_t wb = c->W * sizeof(float);
+    // scratch is laid out [4][ab_slices][plane]; only slice 0 of each plane group was written with nslices=1
+    for (int k = 0; k < 4; ++k) {
+        float* dst = k < 3 ? a3 + (size_t)k * c->W * c->H : b;
+        PSM_CUDA(c, cudaMemcpy2DAsync(dst, wb, c->ab + (size_t)k * c->plane, c->Wp * sizeof(float), wb, c->H,
+                                      cudaMemcpyDeviceToHost, c->stream));
+    }
+    PSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PSM_OK;
+}
+
+int psm_device_ptr(psm_ctx* c, int what, void** ptr, size_t* pitch_elems)
+{
+    if (!c || !ptr) return fail(c, PSM_EINVAL, "null argument");
+    switch (what) {
+    case 0: case 1: *ptr = c->vol[what]; if (pitch_elems) *pitch_elems = c->Wp; return PSM_OK;
+    case 2: case 3: *ptr = c->dis[what - 2]; if (pitch_elems) *pitch_elems = c->W; return PSM_OK;
+    default: return fail(c, PSM_EINVAL, "bad selector %d", what);
+    }
+}
+
+int psm_stage_ms(psm_ctx* c, int stage, float* ms)
+{
+    if (int rc = bind(c)) return rc;
+    if (stage < 0 || stage >= kNumStages || !ms) return fail(c, PSM_EINVAL, "bad stage %d", stage);
+    if (!c->ev_valid[stage]) return fail(c, PSM_ESTATE, "stage %d has not been timed", stage);
+    PSM_CUDA(c, cudaEventSynchronize(c->ev1[stage]));
+    PSM_CUDA(c, cudaEventElapsedTime(ms, c->ev0[stage], c->ev1[stage]));
+    return PSM_OK;
+}
+
+int psm_launch_count(psm_ctx* c, uint64_t* n)
+{
+    if (!c || !n) return fail(c, PSM_EINVAL, "null argument");
+    *n = c->launches;
+    return PSM_OK;
+}
+
+int psm_sync(psm_ctx* c)
+{
+    if (int rc = bind(c)) return rc;
+    PSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PSM_OK;
+}
+
+}  // extern "C"

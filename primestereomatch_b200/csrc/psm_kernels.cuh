@@ -1,0 +1,384 @@
+// psm_kernels.cuh -- ingest, cost-volume construction (CVC), guide precompute, WTA and the
+// unfused "naive" CVF cross-check kernels.  The fused streaming CVF kernel is in
+// psm_cvf_stream.cuh.  All layouts: planes are [H][Wp] float (Wp = W rounded up to 4, so every
+// row is 16-byte aligned); volumes are [d_local][H][Wp] float.
+#pragma once
+#include "psm_common.cuh"
+
+namespace psm {
+
+// ------------------------------------------------------------------------------------------
+// Ingest: interleaved BGR (float or u8) -> 3 planar channels + x-gradient of the gray image.
+// Restates StereoMatch.cpp:193-197 (u8 * (1/255.0f)), CVF.cpp:47 (split) and CVC.cpp:41-46
+// (cvtColor RGB2GRAY on the BGR image, Sobel dx=1 ksize=1 with BORDER_REFLECT_101).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(uint8_t v) { return fmul((float)v, 1 / 255.0f); }
+
+template <typename T>
+__device__ __forceinline__ float gray_at(const T* __restrict__ row, int x, int gray_mode)
+{
+    const float c0 = to_f32(row[3 * x]), c1 = to_f32(row[3 * x + 1]), c2 = to_f32(row[3 * x + 2]);
+    if (gray_mode == 0) return __fmaf_rn(c2, 0.114f, __fmaf_rn(c0, 0.299f, fmul(c1, 0.587f)));
+    return fadd(fadd(fmul(c0, 0.299f), fmul(c1, 0.587f)), fmul(c2, 0.114f));
+}
+
+template <typename T>
+__global__ void ingest_kernel(const T* __restrict__ src, size_t step_bytes, int W, int H, int Wp,
+                              float* __restrict__ I0, float* __restrict__ I1, float* __restrict__ I2,
+                              float* __restrict__ grd, int gray_mode)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= Wp || y >= H) return;
+    const size_t o = (size_t)y * Wp + x;
+    if (x >= W) { I0[o] = 0.f; I1[o] = 0.f; I2[o] = 0.f; grd[o] = 0.f; return; }
+    const T* row = reinterpret_cast<const T*>(reinterpret_cast<const char*>(src) + (size_t)y * step_bytes);
+    I0[o] = to_f32(row[3 * x]);
+    I1[o] = to_f32(row[3 * x + 1]);
+    I2[o] = to_f32(row[3 * x + 2]);
+    const float gr = gray_at(row, reflect101(x + 1, W), gray_mode);
+    const float gl = gray_at(row, reflect101(x - 1, W), gray_mode);
+    grd[o] = fsub(gr, gl);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 CVC.  One thread = 4 consecutive pixels of one row of ONE view; it walks the owned
+// disparities keeping the matched window of the other image in registers (one new scalar load
+// per plane per disparity) and writes one 128-bit store per slice.
+//   left  volume (SIGN=-1): x >= d     ? cost4(L[x], R[x-d]) : border(L[x])   CVC.cpp:122-149
+//   right volume (SIGN=+1): x <  W - d ? cost4(R[x], L[x+d]) : border(R[x])   CVC.cpp:151-179
+// cost4 = CVC.cpp:18-27 (float), border = CVC.cpp:30-39 (double intermediates, BC_32F = 1.0).
+// ------------------------------------------------------------------------------------------
+struct CvcParams {
+    const float* self[4];   // planes of the view being built: c0,c1,c2,grd
+    const float* other[4];  // planes of the matched view
+    float* vol;             // [d_count][H][Wp]
+    int W, H, Wp, d_begin, d_count;
+};
+
+__device__ __forceinline__ float cost4(float l0, float l1, float l2, float lg,
+                                       float r0, float r1, float r2, float rg)
+{
+    const float clr = fadd(fadd(fabsf(fsub(l0, r0)), fabsf(fsub(l1, r1))), fabsf(fsub(l2, r2)));
+    const float grd = fabsf(fsub(lg, rg));
+    return fadd(fmul(0.9f, clr), fmul(fsub(1.0f, 0.9f), grd));
+}
+
+__device__ __forceinline__ float cost_border(float l0, float l1, float l2, float lg)
+{
+    const double s = __dadd_rn(__dadd_rn(fabs(__dsub_rn((double)l0, 1.0)), fabs(__dsub_rn((double)l1, 1.0))),
+                               fabs(__dsub_rn((double)l2, 1.0)));
+    const float clr = (float)s;
+    const float grd = (float)fabs(__dsub_rn((double)lg, 1.0));
+    return fadd(fmul(0.9f, clr), fmul(fsub(1.0f, 0.9f), grd));
+}
+
+template <int SIGN>
+__global__ void __launch_bounds__(128) cvc_kernel(CvcParams P)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x4 >= P.Wp) return;
+    const int W = P.W;
+    const size_t ro = (size_t)y * P.Wp;
+
+    float s[4][4], bord[4];  // [plane][pixel]
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(P.self[c] + ro + x4));
+        s[c][0] = v.x; s[c][1] = v.y; s[c][2] = v.z; s[c][3] = v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bord[j] = cost_border(s[0][j], s[1][j], s[2][j], s[3][j]);
+
+    const float* o0 = P.other[0] + ro;
+    const float* o1 = P.other[1] + ro;
+    const float* o2 = P.other[2] + ro;
+    const float* o3 = P.other[3] + ro;
+    auto clampx = [W](int x) { return x < 0 ? 0 : (x >= W ? W - 1 : x); };
+
+    // window w[c][j] = other[c][x4 + j + SIGN*d]
+    float w[4][4];
+    int d = P.d_begin;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int xo = clampx(x4 + j + SIGN * d);
+        w[0][j] = __ldg(o0 + xo); w[1][j] = __ldg(o1 + xo); w[2][j] = __ldg(o2 + xo); w[3][j] = __ldg(o3 + xo);
+    }
+    const size_t slice = (size_t)P.H * P.Wp;
+    float* out = P.vol + ro + x4;
+#pragma unroll 4
+    for (int dl = 0; dl < P.d_count; ++dl, ++d) {
+        float4 r;
+        float* rp = reinterpret_cast<float*>(&r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = x4 + j;
+            const bool interior = (SIGN < 0) ? (x >= d) : (x < W - d);
+            const float c = cost4(s[0][j], s[1][j], s[2][j], s[3][j], w[0][j], w[1][j], w[2][j], w[3][j]);
+            rp[j] = (x < W) ? (interior ? c : bord[j]) : 0.f;
+        }
+        *reinterpret_cast<float4*>(out + (size_t)dl * slice) = r;
+        // slide the window by one disparity
+        if (SIGN < 0) {
+            const int xo = clampx(x4 - (d + 1));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { w[c][3] = w[c][2]; w[c][2] = w[c][1]; w[c][1] = w[c][0]; }
+            w[0][0] = __ldg(o0 + xo); w[1][0] = __ldg(o1 + xo); w[2][0] = __ldg(o2 + xo); w[3][0] = __ldg(o3 + xo);
+        } else {
+            const int xo = clampx(x4 + 3 + (d + 1));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { w[c][0] = w[c][1]; w[c][1] = w[c][2]; w[c][2] = w[c][3]; }
+            w[0][3] = __ldg(o0 + xo); w[1][3] = __ldg(o1 + xo); w[2][3] = __ldg(o2 + xo); w[3][3] = __ldg(o3 + xo);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact 8x8 box mean of a plane at one pixel: sum of 64 reflected taps in fp64, * 1/64, one
+// rounding to float == cv::boxFilter(CV_32F, Size(8,8)) (anchor (4,4), BORDER_REFLECT_101,
+// double accumulation).  Used by the guide precompute and the naive cross-check kernels.
+// ------------------------------------------------------------------------------------------
+template <typename F>
+__device__ __forceinline__ float box8_direct(F tap, int x, int y, int W, int H)
+{
+    double s = 0.0;
+#pragma unroll 1
+    for (int dy = -kBoxAnchor; dy < kBoxK - kBoxAnchor; ++dy) {
+        const int yy = reflect101(y + dy, H);
+        double rs = 0.0;
+#pragma unroll
+        for (int dx = -kBoxAnchor; dx < kBoxK - kBoxAnchor; ++dx)
+            rs = __dadd_rn(rs, (double)tap(reflect101(x + dx, W), yy));
+        s = __dadd_rn(s, rs);
+    }
+    return (float)__dmul_rn(s, 1.0 / 64.0);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 guide precompute (CVF::preprocess, CVF.cpp:44-70) + the d-independent part of the 3x3
+// solve of GuidedFilter_cv (CVF.cpp:117-126): the symmetric adjugate of (Sigma + eps I) and
+// 1/det.  Separable: pass H writes fp64 horizontal 8-sums of the 9 planes
+// (I_c, I_c*I_c'), pass V finishes the box, forms mean/var and the solve terms.
+// guide planes (each [H][Wp]): 0-2 I, 3-5 mean_I, 6-11 adj (M00,M01,M02,M11,M12,M22), 12 1/det,
+// 13-18 var_I (rr,rg,rb,gg,gb,bb; kept for parity reads).
+// ------------------------------------------------------------------------------------------
+constexpr int kGuideI = 0, kGuideMean = 3, kGuideAdj = 6, kGuideIdet = 12, kGuideVar = 13, kGuidePlanes = 19;
+
+__global__ void guide_hsum_kernel(const float* __restrict__ guide, size_t plane, int W, int H, int Wp,
+                                  double* __restrict__ hs /* [9][H][W] */)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    const float* I0 = guide + (size_t)y * Wp;
+    const float* I1 = I0 + plane;
+    const float* I2 = I1 + plane;
+    double s[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s[k] = 0.0;
+#pragma unroll
+    for (int dx = -kBoxAnchor; dx < kBoxK - kBoxAnchor; ++dx) {
+        const int xx = reflect101(x + dx, W);
+        const float a = __ldg(I0 + xx), b = __ldg(I1 + xx), c = __ldg(I2 + xx);
+        s[0] = __dadd_rn(s[0], (double)a);
+        s[1] = __dadd_rn(s[1], (double)b);
+        s[2] = __dadd_rn(s[2], (double)c);
+        s[3] = __dadd_rn(s[3], (double)fmul(a, a));  // rr   (CVF.cpp:62 multiply)
+        s[4] = __dadd_rn(s[4], (double)fmul(a, b));  // rg
+        s[5] = __dadd_rn(s[5], (double)fmul(a, c));  // rb
+        s[6] = __dadd_rn(s[6], (double)fmul(b, b));  // gg
+        s[7] = __dadd_rn(s[7], (double)fmul(b, c));  // gb
+        s[8] = __dadd_rn(s[8], (double)fmul(c, c));  // bb
+    }
+    const size_t hp = (size_t)H * W;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) hs[k * hp + (size_t)y * W + x] = s[k];
+}
+
+__global__ void guide_finish_kernel(const double* __restrict__ hs, float* __restrict__ guide, size_t plane,
+                                    int W, int H, int Wp)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= Wp) return;
+    const size_t o = (size_t)y * Wp + x;
+    if (x >= W) {
+        for (int k = kGuideMean; k < kGuidePlanes; ++k) guide[k * plane + o] = 0.f;
+        return;
+    }
+    const size_t hp = (size_t)H * W;
+    float m[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int dy = -kBoxAnchor; dy < kBoxK - kBoxAnchor; ++dy)
+            s = __dadd_rn(s, hs[k * hp + (size_t)reflect101(y + dy, H) * W + x]);
+        m[k] = (float)__dmul_rn(s, 1.0 / 64.0);
+    }
+    // var_I[idx] = box(I_c * I_c') - mean_c * mean_c'   (CVF.cpp:60-69)
+    float v[6];
+    v[0] = fsub(m[3], fmul(m[0], m[0]));
+    v[1] = fsub(m[4], fmul(m[0], m[1]));
+    v[2] = fsub(m[5], fmul(m[0], m[2]));
+    v[3] = fsub(m[6], fmul(m[1], m[1]));
+    v[4] = fsub(m[7], fmul(m[1], m[2]));
+    v[5] = fsub(m[8], fmul(m[2], m[2]));
+    // CVF.cpp:108-116
+    const float a11 = fadd(v[0], kGifEps), a12 = v[1], a13 = v[2];
+    const float a21 = v[1], a22 = fadd(v[3], kGifEps), a23 = v[4];
+    const float a31 = v[2], a32 = v[4], a33 = fadd(v[5], kGifEps);
+    // cofactors exactly as written at CVF.cpp:117-146 (the adjugate is symmetric bit-for-bit
+    // because each mirrored entry is the same two products in commuted order)
+    const float M00 = fsub(fmul(a33, a22), fmul(a32, a23));
+    const float M01 = fsub(fmul(a31, a23), fmul(a33, a21));
+    const float M02 = fsub(fmul(a32, a21), fmul(a31, a22));
+    const float M11 = fsub(fmul(a33, a11), fmul(a31, a13));
+    const float M12 = fsub(fmul(a31, a12), fmul(a32, a11));
+    const float M22 = fsub(fmul(a22, a11), fmul(a21, a12));
+    // DET = a11*(a33*a22-a32*a23) - a21*(a33*a12-a32*a13) + a31*(a23*a12-a22*a13)  (CVF.cpp:117-119)
+    const float t1 = fsub(fmul(a33, a12), fmul(a32, a13));
+    const float t2 = fsub(fmul(a23, a12), fmul(a22, a13));
+    float det = fadd(fsub(fmul(a11, M00), fmul(a21, t1)), fmul(a31, t2));
+    det = __fdiv_rn(1.0f, det);  // CVF.cpp:120
+    guide[(kGuideMean + 0) * plane + o] = m[0];
+    guide[(kGuideMean + 1) * plane + o] = m[1];
+    guide[(kGuideMean + 2) * plane + o] = m[2];
+    guide[(kGuideAdj + 0) * plane + o] = M00;
+    guide[(kGuideAdj + 1) * plane + o] = M01;
+    guide[(kGuideAdj + 2) * plane + o] = M02;
+    guide[(kGuideAdj + 3) * plane + o] = M11;
+    guide[(kGuideAdj + 4) * plane + o] = M12;
+    guide[(kGuideAdj + 5) * plane + o] = M22;
+    guide[kGuideIdet * plane + o] = det;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) guide[(kGuideVar + k) * plane + o] = v[k];
+}
+
+// Per-voxel coefficient math shared by every CVF kernel: CVF.cpp:92-95 (cov), :121-146 (a),
+// :152-155 (b).  mp/mIp are the four stage-1 box means at this voxel.
+struct GuidePix { float mI0, mI1, mI2, M00, M01, M02, M11, M12, M22, idet; };
+
+__device__ __forceinline__ void gif_coeffs(float mp, float mIp0, float mIp1, float mIp2, const GuidePix& g,
+                                           float& a0, float& a1, float& a2, float& b)
+{
+    const float c0 = fsub(mIp0, fmul(g.mI0, mp));
+    const float c1 = fsub(mIp1, fmul(g.mI1, mp));
+    const float c2 = fsub(mIp2, fmul(g.mI2, mp));
+    a0 = fmul(g.idet, fadd(fadd(fmul(c0, g.M00), fmul(c1, g.M01)), fmul(c2, g.M02)));
+    a1 = fmul(g.idet, fadd(fadd(fmul(c0, g.M01), fmul(c1, g.M11)), fmul(c2, g.M12)));
+    a2 = fmul(g.idet, fadd(fadd(fmul(c0, g.M02), fmul(c1, g.M12)), fmul(c2, g.M22)));
+    b = fsub(fsub(fsub(mp, fmul(a0, g.mI0)), fmul(a1, g.mI1)), fmul(a2, g.mI2));
+}
+
+// ------------------------------------------------------------------------------------------
+// Naive CVF (PSM_CVF_NAIVE): two unfused passes with direct 64-tap fp64 sums per voxel.
+// Slow by construction (256 loads per voxel per pass); exists as an independent device-side
+// implementation to cross-check the fused streaming kernel and for tiny images.
+// ------------------------------------------------------------------------------------------
+__global__ void cvf_naive_ab_kernel(const float* __restrict__ vol, const float* __restrict__ guide, size_t plane,
+                                    int W, int H, int Wp, int nslices,
+                                    float* __restrict__ ab /* [4][nslices][H][Wp] */)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int dl = blockIdx.z;
+    if (x >= W) return;
+    const float* p = vol + (size_t)dl * plane;
+    const float* I0 = guide;
+    const float* I1 = guide + plane;
+    const float* I2 = guide + 2 * plane;
+    const float mp = box8_direct([&](int xx, int yy) { return p[(size_t)yy * Wp + xx]; }, x, y, W, H);
+    const float m0 = box8_direct([&](int xx, int yy) { const size_t o = (size_t)yy * Wp + xx; return fmul(I0[o], p[o]); }, x, y, W, H);
+    const float m1 = box8_direct([&](int xx, int yy) { const size_t o = (size_t)yy * Wp + xx; return fmul(I1[o], p[o]); }, x, y, W, H);
+    const float m2 = box8_direct([&](int xx, int yy) { const size_t o = (size_t)yy * Wp + xx; return fmul(I2[o], p[o]); }, x, y, W, H);
+    const size_t o = (size_t)y * Wp + x;
+    GuidePix g;
+    g.mI0 = guide[(kGuideMean + 0) * plane + o]; g.mI1 = guide[(kGuideMean + 1) * plane + o]; g.mI2 = guide[(kGuideMean + 2) * plane + o];
+    g.M00 = guide[(kGuideAdj + 0) * plane + o]; g.M01 = guide[(kGuideAdj + 1) * plane + o]; g.M02 = guide[(kGuideAdj + 2) * plane + o];
+    g.M11 = guide[(kGuideAdj + 3) * plane + o]; g.M12 = guide[(kGuideAdj + 4) * plane + o]; g.M22 = guide[(kGuideAdj + 5) * plane + o];
+    g.idet = guide[kGuideIdet * plane + o];
+    float a0, a1, a2, b;
+    gif_coeffs(mp, m0, m1, m2, g, a0, a1, a2, b);
+    const size_t vs = (size_t)nslices * plane;
+    const size_t oo = (size_t)dl * plane + o;
+    ab[oo] = a0; ab[vs + oo] = a1; ab[2 * vs + oo] = a2; ab[3 * vs + oo] = b;
+}
+
+__global__ void cvf_naive_q_kernel(const float* __restrict__ ab, const float* __restrict__ guide, size_t plane,
+                                   int W, int H, int Wp, int nslices, float* __restrict__ vol_out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int dl = blockIdx.z;
+    if (x >= W) return;
+    const size_t vs = (size_t)nslices * plane;
+    const float* a0 = ab + (size_t)dl * plane;
+    const float* a1 = a0 + vs;
+    const float* a2 = a1 + vs;
+    const float* b = a2 + vs;
+    auto tapper = [&](const float* pl) {
+        return box8_direct([&](int xx, int yy) { return pl[(size_t)yy * Wp + xx]; }, x, y, W, H);
+    };
+    const size_t o = (size_t)y * Wp + x;
+    // q = box(b); q += box(a_c) * I_c for c = 0,1,2   (CVF.cpp:157-163)
+    float q = tapper(b);
+    q = fadd(q, fmul(tapper(a0), guide[o]));
+    q = fadd(q, fmul(tapper(a1), guide[plane + o]));
+    q = fadd(q, fmul(tapper(a2), guide[2 * plane + o]));
+    vol_out[(size_t)dl * plane + o] = q;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 WTA (DispSel.cpp:83-109): per pixel argmin over global d in [1, D), strict <, ties -> lowest d,
+// minCost starts at +inf, result 0 when nothing compares below +inf.  One thread = 4 pixels.
+// Emits the u8 map and/or the packed (cost,d) key used by the disparity-sharded reduction.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wta_kernel(const float* __restrict__ vol, int W, int H, int Wp, int d_begin, int d_count,
+                                                  uint8_t* __restrict__ dis /* [H][W] or null */,
+                                                  unsigned long long* __restrict__ keys /* [H][W] or null */)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x4 >= W) return;
+    const size_t plane = (size_t)H * Wp;
+    const float* p = vol + (size_t)y * Wp + x4;
+    float mc[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    int md[4] = {0, 0, 0, 0};
+    int dl = (d_begin == 0) ? 1 : 0;  // global d = 0 is never a candidate (DispSel.cpp:96)
+#pragma unroll 8
+    for (; dl < d_count; ++dl) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(p + (size_t)dl * plane));
+        const int d = d_begin + dl;
+        if (c.x < mc[0]) { mc[0] = c.x; md[0] = d; }
+        if (c.y < mc[1]) { mc[1] = c.y; md[1] = d; }
+        if (c.z < mc[2]) { mc[2] = c.z; md[2] = d; }
+        if (c.w < mc[3]) { mc[3] = c.w; md[3] = d; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = x4 + j;
+        if (x < W) {
+            if (dis) dis[(size_t)y * W + x] = (uint8_t)md[j];
+            if (keys) keys[(size_t)y * W + x] = ((unsigned long long)float_order_key(mc[j]) << 32) | (unsigned)md[j];
+        }
+    }
+}
+
+// Final step of the sharded WTA: min over ranks of the packed keys, low 8 bits -> u8 map.
+__global__ void keys_reduce_kernel(const unsigned long long* __restrict__ gathered, int nranks, size_t npix,
+                                   uint8_t* __restrict__ dis)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    unsigned long long k = gathered[i];
+    for (int r = 1; r < nranks; ++r) {
+        const unsigned long long v = gathered[(size_t)r * npix + i];
+        k = v < k ? v : k;
+    }
+    dis[i] = (uint8_t)(k & 0xffu);
+}
+
+}  // namespace psm
