@@ -166,6 +166,7 @@ def main():
     lp = torch.from_numpy(l).pin_memory()
     rp = torch.from_numpy(r).pin_memory()
     ld_dev, rd_dev = lp.cuda(), rp.cuda()
+    torch.cuda.synchronize()
 
     d_count = D // world
     d_begin = rank * d_count
