@@ -8,7 +8,7 @@
 #include <cstring>
 #include <new>
 
-#include "psm_cvf_stream.cuh"
+#include "psm_cvf_stream2.cuh"
 
 #ifndef PSM_BUILD_FLAGS
 #define PSM_BUILD_FLAGS "unknown"
@@ -35,6 +35,8 @@ struct psm_ctx {
     double* hs = nullptr;                   // guide precompute scratch [9][H][W] fp64
     void* stage_in[2] = {nullptr, nullptr}; // device staging for the interleaved upload
     uint8_t* dis[2] = {nullptr, nullptr};
+    int* strip_list = nullptr;              // streaming kernel: interior strips first, then border strips
+    int n_interior = 0;
     float* ab = nullptr;                    // naive-mode scratch [4][d_count][H][Wp], lazy
     size_t ab_slices = 0;
     cudaEvent_t ev0[kNumStages] = {}, ev1[kNumStages] = {};
@@ -180,6 +182,52 @@ int launch_cvf_stream(psm_ctx* c)
     return PSM_OK;
 }
 
+void fill_cvf_params(psm_ctx* c, CvfParams& P, int slices_per_cta)
+{
+    for (int v = 0; v < 2; ++v) { P.vol_in[v] = c->vol[v]; P.vol_out[v] = c->vol_alt[v]; P.guide[v] = c->guide[v]; }
+    P.W = c->W; P.H = c->H; P.Wp = c->Wp; P.Dloc = c->d_count;
+    P.nstrips = (c->W + kStripOut - 1) / kStripOut;
+    P.ndgroups = (c->d_count + slices_per_cta - 1) / slices_per_cta;
+    int target_rows = 256;
+    const long ctas_1seg = 2L * P.nstrips * P.ndgroups;
+    if (ctas_1seg * (c->H / 256 > 0 ? c->H / 256 : 1) < 148 * 3 * 4) target_rows = 128;
+    plan_segments(c->H, target_rows, &P.nseg, &P.seg_rows);
+}
+
+int launch_cvf_stream2(psm_ctx* c)
+{
+    CvfParams P;
+    fill_cvf_params(c, P, 4);
+    // strip classes: [0, n_int) interior strips, [n_int, nstrips) border strips (device list built once)
+    if (!c->strip_list) {
+        int host[512];
+        int n = 0;
+        if (P.nstrips > 512) return fail(c, PSM_EINVAL, "image too wide (%d strips)", P.nstrips);
+        for (int s = 0; s < P.nstrips; ++s) if (!strip_is_border(s, P.nstrips, c->W)) host[n++] = s;
+        c->n_interior = n;
+        for (int s = 0; s < P.nstrips; ++s) if (strip_is_border(s, P.nstrips, c->W)) host[n++] = s;
+        PSM_CUDA(c, cudaMalloc(&c->strip_list, P.nstrips * sizeof(int)));
+        PSM_CUDA(c, cudaMemcpyAsync(c->strip_list, host, P.nstrips * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        PSM_CUDA(c, cudaStreamSynchronize(c->stream));  // host[] is on this stack frame
+        const size_t smem0 = (size_t)8 * 4 * 128 * sizeof(float4);
+        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+    }
+    const size_t smem = (size_t)8 * 4 * 128 * sizeof(float4);
+    const int n_int = c->n_interior, n_brd = P.nstrips - n_int;
+    if (n_int > 0) {
+        const unsigned grid = 2u * P.nseg * n_int * P.ndgroups;
+        cvf_stream2_kernel<false><<<grid, 128, smem, c->stream>>>(P, c->strip_list, n_int);
+        PSM_LAUNCH_CHECK(c);
+    }
+    if (n_brd > 0) {
+        const unsigned grid = 2u * P.nseg * n_brd * P.ndgroups;
+        cvf_stream2_kernel<true><<<grid, 128, smem, c->stream>>>(P, c->strip_list + n_int, n_brd);
+        PSM_LAUNCH_CHECK(c);
+    }
+    return PSM_OK;
+}
+
 int copy_map_out(psm_ctx* c, const uint8_t* dsrc, uint8_t* dst, size_t step)
 {
     if (!dst || step < (size_t)c->W) return fail(c, PSM_EINVAL, "bad disparity map pointer/step");
@@ -277,6 +325,7 @@ int psm_destroy(psm_ctx* c)
     }
     cudaFree(c->hs);
     cudaFree(c->ab);
+    cudaFree(c->strip_list);
     for (int s = 0; s < kNumStages; ++s) {
         if (c->ev0[s]) cudaEventDestroy(c->ev0[s]);
         if (c->ev1[s]) cudaEventDestroy(c->ev1[s]);
@@ -389,7 +438,12 @@ int psm_cost_filter(psm_ctx* c)
         if (int rc = stage_end(c, 4)) return rc;
     } else {
         if (int rc = stage_begin(c, 4)) return rc;
-        int rc = (c->cvf_variant == 1) ? launch_cvf_stream<2, 2>(c) : launch_cvf_stream<1, 4>(c);
+        int rc;
+        switch (c->cvf_variant) {
+        case 1: rc = launch_cvf_stream<2, 2>(c); break;   // v1, two slices per warp
+        case 2: rc = launch_cvf_stream<1, 4>(c); break;   // v1
+        default: rc = launch_cvf_stream2(c); break;       // v2 (default)
+        }
         if (rc) return rc;
         if (int rc2 = stage_end(c, 4)) return rc2;
     }
