@@ -9,8 +9,8 @@
 //   * BORDER template: interior strips (every column of every lane inside the image) take a path
 //     with plain 128-bit loads and no reflection code at all; only the first/last strip of a row
 //     of strips pays for BORDER_REFLECT_101 (per-lane reflected column tables, scalar gathers).
-//   * all fp32 coefficient math runs on packed f32x2 instructions (FMUL2/FADD2, IEEE RN, never
-//     contracted): two columns per issue slot.
+//   * the fp32 multiplies run on packed f32x2 instructions (FMUL2: two columns per issue slot); adds
+//     stay scalar because ptxas would fuse packed mul+add into FFMA2 (see add2 below).
 //   * loads of a row are issued at the top of the iteration, long before their first use.
 //   * row offsets are 32-bit element offsets from three base pointers.
 #pragma once
@@ -24,10 +24,16 @@ struct f2x2 {  // four columns as two packed pairs
 __device__ __forceinline__ f2x2 from4(const float4& v) { return {make_float2(v.x, v.y), make_float2(v.z, v.w)}; }
 __device__ __forceinline__ float4 to4(const f2x2& v) { return make_float4(v.lo.x, v.lo.y, v.hi.x, v.hi.y); }
 __device__ __forceinline__ f2x2 mul2(const f2x2& a, const f2x2& b) { return {__fmul2_rn(a.lo, b.lo), __fmul2_rn(a.hi, b.hi)}; }
-__device__ __forceinline__ f2x2 add2(const f2x2& a, const f2x2& b) { return {__fadd2_rn(a.lo, b.lo), __fadd2_rn(a.hi, b.hi)}; }
+// NOTE: ptxas (12.9) fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false, which
+// would break bit-exactness against the reference's separate multiply / add.  It does not fuse a
+// packed multiply with SCALAR adds, so every add/sub below is two scalar FADDs on the halves.
+__device__ __forceinline__ f2x2 add2(const f2x2& a, const f2x2& b)
+{
+    return {make_float2(fadd(a.lo.x, b.lo.x), fadd(a.lo.y, b.lo.y)), make_float2(fadd(a.hi.x, b.hi.x), fadd(a.hi.y, b.hi.y))};
+}
 __device__ __forceinline__ f2x2 sub2(const f2x2& a, const f2x2& b)
 {
-    return {__fadd2_rn(a.lo, make_float2(-b.lo.x, -b.lo.y)), __fadd2_rn(a.hi, make_float2(-b.hi.x, -b.hi.y))};
+    return {make_float2(fsub(a.lo.x, b.lo.x), fsub(a.lo.y, b.lo.y)), make_float2(fsub(a.hi.x, b.hi.x), fsub(a.hi.y, b.hi.y))};
 }
 __device__ __forceinline__ float get(const f2x2& v, int j) { return j == 0 ? v.lo.x : (j == 1 ? v.lo.y : (j == 2 ? v.hi.x : v.hi.y)); }
 
