@@ -8,7 +8,7 @@
 #include <cstring>
 #include <new>
 
-#include "psm_cvf_stream2.cuh"
+#include "psm_cvf_stream3.cuh"
 
 #ifndef PSM_BUILD_FLAGS
 #define PSM_BUILD_FLAGS "unknown"
@@ -194,7 +194,8 @@ void fill_cvf_params(psm_ctx* c, CvfParams& P, int slices_per_cta)
     plan_segments(c->H, target_rows, &P.nseg, &P.seg_rows);
 }
 
-int launch_cvf_stream2(psm_ctx* c)
+template <int VER>
+int launch_cvf_stream23(psm_ctx* c)
 {
     CvfParams P;
     fill_cvf_params(c, P, 4);
@@ -212,17 +213,21 @@ int launch_cvf_stream2(psm_ctx* c)
         const size_t smem0 = (size_t)8 * 4 * 128 * sizeof(float4);
         PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
         PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
     }
     const size_t smem = (size_t)8 * 4 * 128 * sizeof(float4);
     const int n_int = c->n_interior, n_brd = P.nstrips - n_int;
     if (n_int > 0) {
         const unsigned grid = 2u * P.nseg * n_int * P.ndgroups;
-        cvf_stream2_kernel<false><<<grid, 128, smem, c->stream>>>(P, c->strip_list, n_int);
+        if (VER == 2) cvf_stream2_kernel<false><<<grid, 128, smem, c->stream>>>(P, c->strip_list, n_int);
+        else cvf_stream3_kernel<false><<<grid, 128, smem, c->stream>>>(P, c->strip_list, n_int);
         PSM_LAUNCH_CHECK(c);
     }
     if (n_brd > 0) {
         const unsigned grid = 2u * P.nseg * n_brd * P.ndgroups;
-        cvf_stream2_kernel<true><<<grid, 128, smem, c->stream>>>(P, c->strip_list + n_int, n_brd);
+        if (VER == 2) cvf_stream2_kernel<true><<<grid, 128, smem, c->stream>>>(P, c->strip_list + n_int, n_brd);
+        else cvf_stream3_kernel<true><<<grid, 128, smem, c->stream>>>(P, c->strip_list + n_int, n_brd);
         PSM_LAUNCH_CHECK(c);
     }
     return PSM_OK;
@@ -442,7 +447,8 @@ int psm_cost_filter(psm_ctx* c)
         switch (c->cvf_variant) {
         case 1: rc = launch_cvf_stream<2, 2>(c); break;   // v1, two slices per warp
         case 2: rc = launch_cvf_stream<1, 4>(c); break;   // v1
-        default: rc = launch_cvf_stream2(c); break;       // v2 (default)
+        case 3: rc = launch_cvf_stream23<2>(c); break;    // v2
+        default: rc = launch_cvf_stream23<3>(c); break;   // v3 (default)
         }
         if (rc) return rc;
         if (int rc2 = stage_end(c, 4)) return rc2;
