@@ -8,7 +8,7 @@
 #include <cstring>
 #include <new>
 
-#include "psm_cvf_stream3.cuh"
+#include "psm_cvf_stream.cuh"
 
 #ifndef PSM_BUILD_FLAGS
 #define PSM_BUILD_FLAGS "unknown"
@@ -35,8 +35,9 @@ struct psm_ctx {
     double* hs = nullptr;                   // guide precompute scratch [9][H][W] fp64
     void* stage_in[2] = {nullptr, nullptr}; // device staging for the interleaved upload
     uint8_t* dis[2] = {nullptr, nullptr};
-    int* strip_list = nullptr;              // streaming kernel: interior strips first, then border strips
-    int n_interior = 0;
+    float* alloc[16] = {};                  // raw cudaMalloc pointers behind the halo-offset pointers above
+    int nalloc = 0;
+    bool cvf_attr_set = false;
     float* ab = nullptr;                    // naive-mode scratch [4][d_count][H][Wp], lazy
     size_t ab_slices = 0;
     cudaEvent_t ev0[kNumStages] = {}, ev1[kNumStages] = {};
@@ -91,6 +92,15 @@ int stage_end(psm_ctx* c, int s)
     return PSM_OK;
 }
 
+// mirror the column halos of `nrows` rows starting at `base` (pointer to row 0, column 0)
+int pad_rows(psm_ctx* c, float* base, size_t nrows)
+{
+    const unsigned blocks = (unsigned)((nrows + 7) / 8);
+    pad_cols_kernel<<<blocks, 256, 0, c->stream>>>(base, nrows, c->W, c->Wp);
+    PSM_LAUNCH_CHECK(c);
+    return PSM_OK;
+}
+
 template <typename T>
 int ingest(psm_ctx* c, const T* l, size_t lstep, const T* r, size_t rstep, bool from_device)
 {
@@ -108,10 +118,11 @@ int ingest(psm_ctx* c, const T* l, size_t lstep, const T* r, size_t rstep, bool 
             dstep = row_bytes;
         }
         float* g = c->guide[v];
-        dim3 blk(128), grd((c->Wp + 127) / 128, c->H);
+        dim3 blk(128), grd((c->W + 3 + 127) / 128, c->H);
         ingest_kernel<T><<<grd, blk, 0, c->stream>>>(dsrc, dstep, c->W, c->H, c->Wp, g, g + c->plane,
                                                       g + 2 * c->plane, c->grd[v], c->gray_mode);
         PSM_LAUNCH_CHECK(c);
+        if (int rc = pad_rows(c, g, (size_t)3 * c->H)) return rc;  // mirrored halo of the 3 guide channels
     }
     c->have_images = true;
     c->guide_valid = false;
@@ -123,7 +134,7 @@ int ensure_guide(psm_ctx* c)
 {
     if (c->guide_valid) return PSM_OK;
     for (int v = 0; v < 2; ++v) {
-        dim3 blk(128), g1((c->W + 127) / 128, c->H), g2((c->Wp + 127) / 128, c->H);
+        dim3 blk(128), g1((c->W + 127) / 128, c->H), g2((c->W + 3 + 127) / 128, c->H);
         guide_hsum_kernel<<<g1, blk, 0, c->stream>>>(c->guide[v], c->plane, c->W, c->H, c->Wp, c->hs);
         PSM_LAUNCH_CHECK(c);
         guide_finish_kernel<<<g2, blk, 0, c->stream>>>(c->hs, c->guide[v], c->plane, c->W, c->H, c->Wp);
@@ -159,77 +170,27 @@ void plan_segments(int H, int target_rows, int* nseg, int* seg_rows)
     *seg_rows = (H + 7) & ~7;
 }
 
-template <int DT, int NW>
 int launch_cvf_stream(psm_ctx* c)
 {
     CvfParams P;
     for (int v = 0; v < 2; ++v) { P.vol_in[v] = c->vol[v]; P.vol_out[v] = c->vol_alt[v]; P.guide[v] = c->guide[v]; }
     P.W = c->W; P.H = c->H; P.Wp = c->Wp; P.Dloc = c->d_count;
     P.nstrips = (c->W + kStripOut - 1) / kStripOut;
-    P.ndgroups = (c->d_count + DT * NW - 1) / (DT * NW);
-    // enough CTAs for several waves over 148 SMs, but segments no shorter than ~128 rows (each
-    // segment pays ~11 warm-up rows)
+    P.ndgroups = (c->d_count + 3) / 4;
+    // enough CTAs for several waves over 148 SMs x 3 resident CTAs, but segments no shorter than
+    // ~128 rows (each segment pays ~11 warm-up rows)
     int target_rows = 256;
     const long ctas_1seg = 2L * P.nstrips * P.ndgroups;
     if (ctas_1seg * (c->H / 256 > 0 ? c->H / 256 : 1) < 148 * 3 * 4) target_rows = 128;
     plan_segments(c->H, target_rows, &P.nseg, &P.seg_rows);
-    const size_t smem = (size_t)8 * 4 * DT * NW * 32 * sizeof(float4);
-    auto kern = cvf_stream_kernel<DT, NW>;
-    PSM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)8 * 4 * kCvfThreads * sizeof(float4);
+    if (!c->cvf_attr_set) {
+        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->cvf_attr_set = true;
+    }
     const unsigned grid = 2u * P.nseg * P.nstrips * P.ndgroups;
-    kern<<<grid, NW * 32, smem, c->stream>>>(P);
+    cvf_stream_kernel<<<grid, kCvfThreads, smem, c->stream>>>(P);
     PSM_LAUNCH_CHECK(c);
-    return PSM_OK;
-}
-
-void fill_cvf_params(psm_ctx* c, CvfParams& P, int slices_per_cta)
-{
-    for (int v = 0; v < 2; ++v) { P.vol_in[v] = c->vol[v]; P.vol_out[v] = c->vol_alt[v]; P.guide[v] = c->guide[v]; }
-    P.W = c->W; P.H = c->H; P.Wp = c->Wp; P.Dloc = c->d_count;
-    P.nstrips = (c->W + kStripOut - 1) / kStripOut;
-    P.ndgroups = (c->d_count + slices_per_cta - 1) / slices_per_cta;
-    int target_rows = 256;
-    const long ctas_1seg = 2L * P.nstrips * P.ndgroups;
-    if (ctas_1seg * (c->H / 256 > 0 ? c->H / 256 : 1) < 148 * 3 * 4) target_rows = 128;
-    plan_segments(c->H, target_rows, &P.nseg, &P.seg_rows);
-}
-
-template <int VER>
-int launch_cvf_stream23(psm_ctx* c)
-{
-    CvfParams P;
-    fill_cvf_params(c, P, 4);
-    // strip classes: [0, n_int) interior strips, [n_int, nstrips) border strips (device list built once)
-    if (!c->strip_list) {
-        int host[512];
-        int n = 0;
-        if (P.nstrips > 512) return fail(c, PSM_EINVAL, "image too wide (%d strips)", P.nstrips);
-        for (int s = 0; s < P.nstrips; ++s) if (!strip_is_border(s, P.nstrips, c->W)) host[n++] = s;
-        c->n_interior = n;
-        for (int s = 0; s < P.nstrips; ++s) if (strip_is_border(s, P.nstrips, c->W)) host[n++] = s;
-        PSM_CUDA(c, cudaMalloc(&c->strip_list, P.nstrips * sizeof(int)));
-        PSM_CUDA(c, cudaMemcpyAsync(c->strip_list, host, P.nstrips * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        PSM_CUDA(c, cudaStreamSynchronize(c->stream));  // host[] is on this stack frame
-        const size_t smem0 = (size_t)8 * 4 * 128 * sizeof(float4);
-        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-    }
-    const size_t smem = (size_t)8 * 4 * 128 * sizeof(float4);
-    const int n_int = c->n_interior, n_brd = P.nstrips - n_int;
-    if (n_int > 0) {
-        const unsigned grid = 2u * P.nseg * n_int * P.ndgroups;
-        if (VER == 2) cvf_stream2_kernel<false><<<grid, 128, smem, c->stream>>>(P, c->strip_list, n_int);
-        else cvf_stream3_kernel<false><<<grid, 128, smem, c->stream>>>(P, c->strip_list, n_int);
-        PSM_LAUNCH_CHECK(c);
-    }
-    if (n_brd > 0) {
-        const unsigned grid = 2u * P.nseg * n_brd * P.ndgroups;
-        if (VER == 2) cvf_stream2_kernel<true><<<grid, 128, smem, c->stream>>>(P, c->strip_list + n_int, n_brd);
-        else cvf_stream3_kernel<true><<<grid, 128, smem, c->stream>>>(P, c->strip_list + n_int, n_brd);
-        PSM_LAUNCH_CHECK(c);
-    }
     return PSM_OK;
 }
 
@@ -272,7 +233,7 @@ int psm_create_sharded(psm_ctx** out, int width, int height, int max_disp, int d
     if (device < 0 || device >= ndev) return fail(nullptr, PSM_ECUDA, "CUDA device %d not available (%d devices)", device, ndev);
     psm_ctx* c = new (std::nothrow) psm_ctx();
     if (!c) return fail(nullptr, PSM_ENOMEM, "out of host memory");
-    c->W = width; c->H = height; c->Wp = (width + 3) & ~3; c->D = max_disp;
+    c->W = width; c->H = height; c->Wp = pitch_for_width(width); c->D = max_disp;
     c->d_begin = d_begin; c->d_count = d_count; c->device = device;
     c->plane = (size_t)c->H * c->Wp;
     auto bail = [&](int code) {
@@ -291,16 +252,26 @@ int psm_create_sharded(psm_ctx** out, int width, int height, int max_disp, int d
     PSM_CREATE_CUDA(cudaSetDevice(device));
     PSM_CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
-    const size_t vol_bytes = (size_t)d_count * c->plane * sizeof(float);
+    // every float buffer is allocated with kPadLeft floats in front so that the (row 0, column 0)
+    // pointer may be indexed at negative columns (left halo of row 0); rows are Wp floats apart
+    auto halo_alloc = [&](float** out, size_t rows) -> cudaError_t {
+        float* raw = nullptr;
+        const size_t n = rows * (size_t)c->Wp + kPadLeft + 32;
+        cudaError_t e = cudaMalloc(&raw, n * sizeof(float));
+        if (e != cudaSuccess) return e;
+        c->alloc[c->nalloc++] = raw;
+        e = cudaMemsetAsync(raw, 0, n * sizeof(float), c->stream);  // DispEst.cpp:31-37 zero-init
+        *out = raw + kPadLeft;
+        return e;
+    };
+    const size_t vol_rows = (size_t)d_count * c->H;
     for (int v = 0; v < 2; ++v) {
-        PSM_CREATE_CUDA(cudaMalloc(&c->guide[v], kGuidePlanes * c->plane * sizeof(float)));
-        PSM_CREATE_CUDA(cudaMalloc(&c->grd[v], c->plane * sizeof(float)));
-        PSM_CREATE_CUDA(cudaMalloc(&c->vol[v], vol_bytes));
-        PSM_CREATE_CUDA(cudaMalloc(&c->vol_alt[v], vol_bytes));
+        PSM_CREATE_CUDA(halo_alloc(&c->guide[v], (size_t)kGuidePlanes * c->H));
+        PSM_CREATE_CUDA(halo_alloc(&c->grd[v], (size_t)c->H));
+        PSM_CREATE_CUDA(halo_alloc(&c->vol[v], vol_rows));
+        PSM_CREATE_CUDA(halo_alloc(&c->vol_alt[v], vol_rows));
         PSM_CREATE_CUDA(cudaMalloc(&c->stage_in[v], (size_t)c->W * c->H * 3 * sizeof(float)));
         PSM_CREATE_CUDA(cudaMalloc(&c->dis[v], (size_t)c->W * c->H));
-        PSM_CREATE_CUDA(cudaMemsetAsync(c->vol[v], 0, vol_bytes, c->stream));  // DispEst.cpp:31-37 zero-init
-        PSM_CREATE_CUDA(cudaMemsetAsync(c->vol_alt[v], 0, vol_bytes, c->stream));
         PSM_CREATE_CUDA(cudaMemsetAsync(c->dis[v], 0, (size_t)c->W * c->H, c->stream));
     }
     PSM_CREATE_CUDA(cudaMalloc(&c->hs, (size_t)9 * c->W * c->H * sizeof(double)));
@@ -324,13 +295,10 @@ int psm_destroy(psm_ctx* c)
     if (!c) return PSM_OK;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    for (int v = 0; v < 2; ++v) {
-        cudaFree(c->guide[v]); cudaFree(c->grd[v]); cudaFree(c->vol[v]); cudaFree(c->vol_alt[v]);
-        cudaFree(c->stage_in[v]); cudaFree(c->dis[v]);
-    }
+    for (int i = 0; i < c->nalloc; ++i) cudaFree(c->alloc[i]);
+    for (int v = 0; v < 2; ++v) { cudaFree(c->stage_in[v]); cudaFree(c->dis[v]); }
     cudaFree(c->hs);
     cudaFree(c->ab);
-    cudaFree(c->strip_list);
     for (int s = 0; s < kNumStages; ++s) {
         if (c->ev0[s]) cudaEventDestroy(c->ev0[s]);
         if (c->ev1[s]) cudaEventDestroy(c->ev1[s]);
@@ -412,10 +380,11 @@ int psm_cost_const(psm_ctx* c)
         P.other[3] = c->grd[1 - v];
         P.vol = c->vol[v];
         P.W = c->W; P.H = c->H; P.Wp = c->Wp; P.d_begin = c->d_begin; P.d_count = c->d_count;
-        dim3 blk(128), grd((c->Wp / 4 + 127) / 128, c->H);
+        dim3 blk(128), grd((((c->W + 3) / 4) + 127) / 128, c->H);
         if (v == PSM_LEFT) cvc_kernel<-1><<<grd, blk, 0, c->stream>>>(P);
         else cvc_kernel<+1><<<grd, blk, 0, c->stream>>>(P);
         PSM_LAUNCH_CHECK(c);
+        if (int rc = pad_rows(c, c->vol[v], (size_t)c->d_count * c->H)) return rc;  // mirrored halo of every slice row
     }
     c->have_cvc = true;
     return stage_end(c, 1);
@@ -443,13 +412,7 @@ int psm_cost_filter(psm_ctx* c)
         if (int rc = stage_end(c, 4)) return rc;
     } else {
         if (int rc = stage_begin(c, 4)) return rc;
-        int rc;
-        switch (c->cvf_variant) {
-        case 1: rc = launch_cvf_stream<2, 2>(c); break;   // v1, two slices per warp
-        case 2: rc = launch_cvf_stream<1, 4>(c); break;   // v1
-        case 3: rc = launch_cvf_stream23<2>(c); break;    // v2
-        default: rc = launch_cvf_stream23<3>(c); break;   // v3 (default)
-        }
+        int rc = launch_cvf_stream(c);
         if (rc) return rc;
         if (int rc2 = stage_end(c, 4)) return rc2;
     }
@@ -542,6 +505,7 @@ int psm_write_cost_slice(psm_ctx* c, int view, int d, const float* src, size_t s
     if (!src || src_step < (size_t)c->W * sizeof(float)) return fail(c, PSM_EINVAL, "bad src/step");
     PSM_CUDA(c, cudaMemcpy2DAsync(c->vol[view] + (size_t)(d - c->d_begin) * c->plane, c->Wp * sizeof(float), src,
                                   src_step, c->W * sizeof(float), c->H, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = pad_rows(c, c->vol[view] + (size_t)(d - c->d_begin) * c->plane, (size_t)c->H)) return rc;
     PSM_CUDA(c, cudaStreamSynchronize(c->stream));
     c->have_cvc = true;  // caller-provided raw costs may be filtered
     return PSM_OK;

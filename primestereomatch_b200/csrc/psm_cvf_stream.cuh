@@ -1,63 +1,87 @@
 // psm_cvf_stream.cuh -- K3: the fused streaming guided-image-filter kernel (the graded kernel).
 //
-// One launch filters every owned slice of both cost volumes:  q = GuidedFilter_cv(I, p)
-// (/root/reference/src/CVF.cpp:72-165) with both 8x8 box stages chained on-chip, so HBM sees
-// p once (read) and q once (write) per voxel; a, b, the eight box means and all products never
-// leave the SM.
+// q = GuidedFilter_cv(I, p) (/root/reference/src/CVF.cpp:72-165) for every owned slice of both cost
+// volumes in ONE pass over HBM: p is read once and q written once per voxel; the two chained 8x8
+// box stages, a, b, all products and all means stay on the SM.  The reference runs ~90 Mat-sized
+// passes per slice for the same result.
 //
-// Decomposition (B200-first, not the reference's per-slice Mat pipeline):
-//   * a WARP owns a strip of 128 input columns (each lane 4 consecutive columns -> 128-bit loads)
-//     of DT disparity slices and streams down the rows of one row segment;
-//   * stage-1 vertical 8-row sums of p, I0*p, I1*p, I2*p are fp64 running sums in registers
-//     (add newest row, subtract oldest row; both come straight from the read-only raw volume);
-//   * the horizontal 8-column sums are formed from per-lane prefix/suffix sums of the 4 owned
-//     columns plus 4 fp64 warp shuffles per box (lane+1 total, lane+2 prefixes);
-//   * a,b for the row are computed in fp32 with the reference's exact operation order and
-//     pushed into a per-thread 8-row ring in shared memory (the only on-chip history needed);
-//   * stage-2 vertical sums of a0,a1,a2,b are fp64 running sums fed from the registers (newest)
-//     and the ring (oldest); horizontal sums as in stage 1; q is written with one 128-bit store.
-//   All box sums are fp64 (== cv::boxFilter's double accumulation, order-independent in practice),
-//   all fp32 arithmetic is unfused round-to-nearest: q is bit-exact against the oracle.
+// Numerics (bit-exact against the oracle):
+//   * cv::boxFilter on CV_32F accumulates in double; an fp64 sum of 64 floats is exact unless the
+//     window spans > 2^23 in magnitude, so any summation order gives the same float after the one
+//     final rounding.  All eight box sums here are fp64: running column sums (+ newest row,
+//     - oldest row) and 8-wide row sums, scaled by 1/64 in fp64, rounded once to float.
+//   * every fp32 operation is a separate IEEE round-to-nearest op in the reference's order
+//     (CVF.cpp:87-163).  Multiplies of two columns share one FMUL2; adds stay scalar because
+//     ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false.
 //
-// Column bookkeeping for strip s (X0 = 112*s, c0 = X0 - 8), lane l:
-//   input  columns  c0+4l   .. c0+4l+3    (p, I)
-//   a,b    columns  c0+4l+4 .. c0+4l+7    (valid for l <= 29; window [x-4, x+3] of the inputs)
-//   output columns  c0+4l+8 .. c0+4l+11   (valid for l <= 27)  ==  X0+4l .. X0+4l+3
-// Borders: input loads reflect (BORDER_REFLECT_101) in x and y; a,b at columns outside [0,W)
-// are replaced by the reflected columns' values (lane shuffles, border strips only); a,b rows
-// outside [0,H) are handled by the running-sum schedule (top: weights 1,2,2,2,1; bottom: three
-// virtual iterations fed from the ring).
+// Work decomposition (B200-first; nothing like the reference's per-slice Mat pipeline):
+//   warp   = one strip of 128 input columns (112 output columns) of ONE disparity slice, one row segment
+//   lane   = 4 consecutive columns -> every global access is a 128-bit load/store
+//   CTA    = 4 warps = 4 consecutive slices of the same strip and segment (guide rows hit in L1)
+//   stage 1: S1[4 boxes][4 cols] fp64 running column sums of p, I0*p, I1*p, I2*p;
+//            row sums = per-lane prefix/suffix sums + 4 fp64 shuffles per box (lane+1 total, lane+2 prefixes)
+//   a,b    : CVF.cpp:92-155 with the d-independent adjugate / 1/det precomputed per pixel (K2)
+//   ring   : thread-private 8-row history of a0,a1,a2,b in shared memory (512 B per thread);
+//            the only on-chip history: stage-1 "oldest rows" are re-read from the raw volume (L1/L2)
+//   stage 2: S2[4 planes][4 cols] fp64 running column sums of a0,a1,a2,b (newest from registers,
+//            oldest from the ring); row sums as in stage 1; q = box(b) + sum_c box(a_c) * I_c
+//
+// Column bookkeeping of strip s (X0 = first output column, 112*s; the last strip is shifted left
+// to end at the image edge), lane l:
+//   input  columns X0-8+4l .. +3   (p, I)                  halo columns come from the mirrored halo
+//   a,b    columns X0-4+4l .. +3   (valid for l <= 29)     of the padded layout (psm_kernels.cuh)
+//   output columns X0  +4l .. +3   (valid for l <= 27)
+// a,b at columns outside [0,W) must be the REFLECTED a,b (cv::boxFilter reflects its input, which
+// for the second stage is a,b) -- not what stage 1 computes there from mirrored p (the 8-wide window
+// is asymmetric) -- so border strips overwrite those entries by lane shuffles.
+// Rows: the top of the image uses weights 1,2,2,2,1 for the first window, the bottom feeds three
+// virtual rows from the ring; input rows reflect by index.  These special cases live in
+// generic_step; the bulk of the rows run steady_step, which has no conditionals at all.
 #pragma once
 #include "psm_kernels.cuh"
 
 namespace psm {
 
-constexpr int kStripOut = 112;   // output columns per warp
-constexpr int kStripIn = 128;    // input columns per warp
-// warps per CTA = template parameter NW (each warp a different disparity group of the same strip)
+constexpr int kStripOut = 112;  // output columns per warp
+constexpr int kStripIn = 128;   // input columns per warp
+constexpr int kCvfThreads = 128;
 
 struct CvfParams {
-    const float* vol_in[2];   // raw volumes  [Dloc][H][Wp]
+    const float* vol_in[2];   // raw volumes  [Dloc][H][Wp]   (pointer to row 0, column 0)
     float* vol_out[2];        // filtered volumes
     const float* guide[2];    // guide planes [kGuidePlanes][H][Wp]
     int W, H, Wp, Dloc;
     int nstrips, nseg, seg_rows, ndgroups;
 };
 
-template <typename T> __device__ __forceinline__ T shfl_down_t(T v, int delta)
+struct f2x2 { float2 lo, hi; };  // four columns as two packed pairs
+__device__ __forceinline__ f2x2 from4(const float4& v) { return {make_float2(v.x, v.y), make_float2(v.z, v.w)}; }
+__device__ __forceinline__ float4 to4(const f2x2& v) { return make_float4(v.lo.x, v.lo.y, v.hi.x, v.hi.y); }
+__device__ __forceinline__ f2x2 mul2(const f2x2& a, const f2x2& b) { return {__fmul2_rn(a.lo, b.lo), __fmul2_rn(a.hi, b.hi)}; }
+__device__ __forceinline__ f2x2 add2(const f2x2& a, const f2x2& b)
 {
-    return __shfl_down_sync(0xffffffffu, v, delta);
+    return {make_float2(fadd(a.lo.x, b.lo.x), fadd(a.lo.y, b.lo.y)), make_float2(fadd(a.hi.x, b.hi.x), fadd(a.hi.y, b.hi.y))};
 }
-
-// 8-wide horizontal window sums from the 4 owned column sums c[0..3]:
-// h[j] = sum of columns (4l+j) .. (4l+j+7)  = suffix_l[j..3] + total_{l+1} + prefix_{l+2}[0..j-1]
-template <typename T>
-__device__ __forceinline__ void hsum8(const T c[4], T h[4])
+__device__ __forceinline__ f2x2 sub2(const f2x2& a, const f2x2& b)
 {
-    const T P1 = c[0], P2 = c[0] + c[1], P3 = P2 + c[2], Tt = P3 + c[3];
-    const T S1 = c[3], S2 = c[2] + c[3], S3 = c[1] + S2;
-    const T Tn = shfl_down_t(Tt, 1);
-    const T Q1 = shfl_down_t(P1, 2), Q2 = shfl_down_t(P2, 2), Q3 = shfl_down_t(P3, 2);
+    return {make_float2(fsub(a.lo.x, b.lo.x), fsub(a.lo.y, b.lo.y)), make_float2(fsub(a.hi.x, b.hi.x), fsub(a.hi.y, b.hi.y))};
+}
+template <int J> __device__ __forceinline__ float get(const f2x2& v)
+{
+    return J == 0 ? v.lo.x : (J == 1 ? v.lo.y : (J == 2 ? v.hi.x : v.hi.y));
+}
+__device__ __forceinline__ float get(const f2x2& v, int j) { return j == 0 ? v.lo.x : (j == 1 ? v.lo.y : (j == 2 ? v.hi.x : v.hi.y)); }
+
+// 8-wide window sums from the 4 owned column sums c[0..3]:
+// h[j] = columns (4l+j) .. (4l+j+7) = suffix_l[j..3] + total_{l+1} + prefix_{l+2}[0..j-1]
+__device__ __forceinline__ void hsum8(const double c[4], double h[4])
+{
+    const double P1 = c[0], P2 = c[0] + c[1], P3 = P2 + c[2], Tt = P3 + c[3];
+    const double S1 = c[3], S2 = c[2] + c[3], S3 = c[1] + S2;
+    const double Tn = __shfl_down_sync(0xffffffffu, Tt, 1);
+    const double Q1 = __shfl_down_sync(0xffffffffu, P1, 2);
+    const double Q2 = __shfl_down_sync(0xffffffffu, P2, 2);
+    const double Q3 = __shfl_down_sync(0xffffffffu, P3, 2);
     h[0] = Tt + Tn;
     h[1] = (S3 + Tn) + Q1;
     h[2] = (S2 + Tn) + Q2;
@@ -66,213 +90,258 @@ __device__ __forceinline__ void hsum8(const T c[4], T h[4])
 
 __device__ __forceinline__ float mean64(double s) { return (float)__dmul_rn(s, 1.0 / 64.0); }
 
-template <int DT, int NW>
-__global__ void __launch_bounds__(NW * 32)
+__device__ __forceinline__ float4 ldg4(const float* __restrict__ p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__global__ void __launch_bounds__(kCvfThreads, 3)
 cvf_stream_kernel(const CvfParams P)
 {
-    extern __shared__ float4 ring[];  // [8 slots][4 planes][DT][blockDim.x] float4 (thread-private columns)
+    extern __shared__ float4 ring[];  // [8 slots][4 planes][128 threads]
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    constexpr int nthr = NW * 32;
+    constexpr int nthr = kCvfThreads;
 
     int b = blockIdx.x;
     const int dgroup = b % P.ndgroups; b /= P.ndgroups;
     const int strip = b % P.nstrips;   b /= P.nstrips;
     const int seg = b % P.nseg;
     const int view = b / P.nseg;
+    const int dlc = dgroup * 4 + warp;
+    if (dlc >= P.Dloc) return;  // warps never synchronise with each other
 
-    const int dbase = (dgroup * NW + warp) * DT;
-    if (dbase >= P.Dloc) return;  // warps are independent: no block-level barrier anywhere below
-
-    const int W = P.W, H = P.H, Wp = P.Wp;
-    const size_t plane = (size_t)H * Wp;
-    const float* __restrict__ G = P.guide[view];
-    const float* __restrict__ vin = P.vol_in[view];
-    float* __restrict__ vout = P.vol_out[view];
-
-    // the last strip is shifted left so that it ends at the image edge (its columns that the
-    // previous strip already produces are not stored again)
+    const int W = P.W, H = P.H;
+    const unsigned Wp = (unsigned)P.Wp;
+    const unsigned plane = (unsigned)H * Wp;
     const int out_lo = strip * kStripOut;
     const int X0 = (strip == P.nstrips - 1 && strip > 0) ? ((W - kStripOut + 3) & ~3) : out_lo;
-    const int cin = X0 - 8 + 4 * lane;  // first owned input column
-    const int ca = cin + 4;             // first a,b column
-    const int co = cin + 8;             // first output column
+    const int cin = X0 - 8 + 4 * lane;
+    const float* __restrict__ Gi = P.guide[view] + cin;                         // guide, input columns
+    const float* __restrict__ Ga = P.guide[view] + cin + 4;                     // guide, a,b columns
+    const float* __restrict__ Go = P.guide[view] + cin + 8;                     // guide, output columns
+    const float* __restrict__ vin = P.vol_in[view] + (size_t)dlc * plane + cin;
+    float* __restrict__ vout = P.vol_out[view] + (size_t)dlc * plane + cin + 8;
+    const bool store_ok = lane <= 27 && cin + 8 < W && cin + 8 >= out_lo;
 
-    int dl[DT];
-    bool dvalid[DT];
-#pragma unroll
-    for (int k = 0; k < DT; ++k) { dvalid[k] = dbase + k < P.Dloc; dl[k] = dvalid[k] ? dbase + k : P.Dloc - 1; }
-
-    // ---- a,b column reflection plan (only strips that touch an image border) -----------------
-    const bool strip_fix = (X0 == 0) || (X0 + kStripOut + 3 >= W);  // warp-uniform
-    int fix_lane[4], fix_elem[4];
-    bool fix_need[4];
+    // ---- x-reflection plan for a,b (strips whose a,b columns X0-4 .. X0+115 leave the image) ----
+    const bool fix_left = X0 == 0;
+    const bool fix_right = X0 + 115 >= W;
+    int fix_src[4];               // source lane of element j (this lane's a,b column X0-4+4l+j mirrored into the image)
+    unsigned maskL = 0, maskR = 0;  // bit j: element j lies left of column 0 / right of column W-1
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int xa = ca + j;
-        fix_need[j] = (xa < 0) || (xa >= W);
-        const int r = reflect101(xa, W) - (X0 - 4);  // offset inside the warp's a,b columns
-        int sl = r >> 2;
-        sl = sl < 0 ? 0 : (sl > 31 ? 31 : sl);
-        fix_lane[j] = sl;
-        fix_elem[j] = r & 3;
+        const int xa = cin + 4 + j;
+        const int r = reflect101(xa < -4 ? -4 : (xa > W + 2 ? W + 2 : xa), W) - (X0 - 4);
+        fix_src[j] = (r >> 2) & 31;
+        maskL |= (fix_left && xa < 0) ? (1u << j) : 0u;
+        maskR |= (fix_right && xa >= W && xa <= W + 2) ? (1u << j) : 0u;
     }
+    // which element of the source lane: left (8-j)&3, right (2(W-1)-j)&3 -- uniform per side, so the
+    // source lane (which does not know who reads it) can put the right element on the wire
+    const int eR = (2 * (W - 1)) & 3;
 
-    // ---- row schedule -----------------------------------------------------------------------
     const int Y0 = seg * P.seg_rows;
     const int Y1 = min(H, Y0 + P.seg_rows);
     const bool top = (Y0 == 0);
     const bool bottom = (Y1 == H);
-    const int T0 = top ? 0 : Y0 - 4;                 // first a,b row computed
-    const int Tlast = bottom ? H - 1 : Y1 + 2;       // last real a,b row
-    const int Tend = bottom ? H + 2 : Tlast;         // last iteration (virtual rows at the bottom)
+    const int T0 = top ? 0 : Y0 - 4;              // first a,b row
+    const int Tlast = bottom ? H - 1 : Y1 + 2;    // last real a,b row
+    const int Tend = bottom ? H + 2 : Tlast;      // last step (three virtual rows below the image)
 
-    double S1[DT][4][4];  // [slice][box: p, I0p, I1p, I2p][column]
-    double S2[DT][4][4];  // [slice][plane: a0, a1, a2, b][column]
+    double S1[4][4], S2[4][4];
 #pragma unroll
-    for (int k = 0; k < DT; ++k)
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { S1[q][j] = 0.0; S2[q][j] = 0.0; }
+
+    struct RowIn { float4 p, i0, i1, i2; };
+    auto load_at = [&](unsigned ro) {
+        RowIn x;
+        x.p = ldg4(vin + ro);
+        x.i0 = ldg4(Gi + ro);
+        x.i1 = ldg4(Gi + plane + ro);
+        x.i2 = ldg4(Gi + 2 * plane + ro);
+        return x;
+    };
+    auto load_row = [&](int r) { return load_at((unsigned)reflect101(r, H) * Wp); };
+    auto add_row = [&](const RowIn& x) {
+        const f2x2 p = from4(x.p);
+        const f2x2 m0 = mul2(from4(x.i0), p), m1 = mul2(from4(x.i1), p), m2 = mul2(from4(x.i2), p);  // CVF.cpp:87
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            S1[0][j] = __dadd_rn(S1[0][j], (double)get(p, j));
+            S1[1][j] = __dadd_rn(S1[1][j], (double)get(m0, j));
+            S1[2][j] = __dadd_rn(S1[2][j], (double)get(m1, j));
+            S1[3][j] = __dadd_rn(S1[3][j], (double)get(m2, j));
+        }
+    };
+    auto sub_row = [&](const RowIn& x) {
+        const f2x2 p = from4(x.p);
+        const f2x2 m0 = mul2(from4(x.i0), p), m1 = mul2(from4(x.i1), p), m2 = mul2(from4(x.i2), p);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            S1[0][j] = __dsub_rn(S1[0][j], (double)get(p, j));
+            S1[1][j] = __dsub_rn(S1[1][j], (double)get(m0, j));
+            S1[2][j] = __dsub_rn(S1[2][j], (double)get(m1, j));
+            S1[3][j] = __dsub_rn(S1[3][j], (double)get(m2, j));
+        }
+    };
+    auto load_guide = [&](unsigned ro, float4 (&g4)[10]) {
+#pragma unroll
+        for (int q = 0; q < 10; ++q) g4[q] = ldg4(Ga + (unsigned)(kGuideMean + q) * plane + ro);
+    };
+
+    // stage-1 row sums -> means -> cov -> a,b (CVF.cpp:81-155), then the x-reflection of a,b
+    auto coeffs = [&](const float4 (&g4)[10], f2x2 (&av)[4]) {
+        double h[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hsum8(S1[q], h[q]);
+        f2x2 m[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
+            m[q] = {make_float2(mean64(h[q][0]), mean64(h[q][1])), make_float2(mean64(h[q][2]), mean64(h[q][3]))};
+        const f2x2 mI0 = from4(g4[0]), mI1 = from4(g4[1]), mI2 = from4(g4[2]);
+        const f2x2 M00 = from4(g4[3]), M01 = from4(g4[4]), M02 = from4(g4[5]);
+        const f2x2 M11 = from4(g4[6]), M12 = from4(g4[7]), M22 = from4(g4[8]);
+        const f2x2 idet = from4(g4[9]);
+        const f2x2 c0 = sub2(m[1], mul2(mI0, m[0]));   // CVF.cpp:92-95
+        const f2x2 c1 = sub2(m[2], mul2(mI1, m[0]));
+        const f2x2 c2 = sub2(m[3], mul2(mI2, m[0]));
+        av[0] = mul2(idet, add2(add2(mul2(c0, M00), mul2(c1, M01)), mul2(c2, M02)));  // CVF.cpp:121-146
+        av[1] = mul2(idet, add2(add2(mul2(c0, M01), mul2(c1, M11)), mul2(c2, M12)));
+        av[2] = mul2(idet, add2(add2(mul2(c0, M02), mul2(c1, M12)), mul2(c2, M22)));
+        av[3] = sub2(sub2(sub2(m[0], mul2(av[0], mI0)), mul2(av[1], mI1)), mul2(av[2], mI2));  // CVF.cpp:152-155
+        if (fix_left | fix_right) {  // warp-uniform
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { S1[k][q][j] = 0.0; S2[k][q][j] = 0.0; }
-
-    // add (sign=+1) or remove (sign=-1) one input row from the stage-1 column sums
-    auto feed = [&](int r, const double sign) {
-        const int rr = reflect101(r, H);
-        const size_t ro = (size_t)rr * Wp;
-        const float4 i0 = load_row4(G + ro, cin, W);
-        const float4 i1 = load_row4(G + plane + ro, cin, W);
-        const float4 i2 = load_row4(G + 2 * plane + ro, cin, W);
+            for (int q = 0; q < 4; ++q) {
+                const float e[4] = {av[q].lo.x, av[q].lo.y, av[q].hi.x, av[q].hi.y};
+                float r[4] = {e[0], e[1], e[2], e[3]};
+                if (fix_left) {
 #pragma unroll
-        for (int k = 0; k < DT; ++k) {
-            const float4 p4 = load_row4(vin + (size_t)dl[k] * plane + ro, cin, W);
+                    for (int j = 0; j < 4; ++j) {
+                        const float v = __shfl_sync(0xffffffffu, e[(8 - j) & 3], fix_src[j]);
+                        if ((maskL >> j) & 1u) r[j] = v;
+                    }
+                }
+                if (fix_right) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float p = comp(p4, j);
-                S1[k][0][j] = __fma_rn(sign, (double)p, S1[k][0][j]);  // +-1 * x is exact: plain add/sub
-                S1[k][1][j] = __fma_rn(sign, (double)fmul(comp(i0, j), p), S1[k][1][j]);  // CVF.cpp:87 multiply
-                S1[k][2][j] = __fma_rn(sign, (double)fmul(comp(i1, j), p), S1[k][2][j]);
-                S1[k][3][j] = __fma_rn(sign, (double)fmul(comp(i2, j), p), S1[k][3][j]);
+                    for (int j = 0; j < 4; ++j) {
+                        const int er = (eR - j) & 3;
+                        const float sv = er == 0 ? e[0] : (er == 1 ? e[1] : (er == 2 ? e[2] : e[3]));
+                        const float v = __shfl_sync(0xffffffffu, sv, fix_src[j]);
+                        if ((maskR >> j) & 1u) r[j] = v;
+                    }
+                }
+                av[q] = {make_float2(r[0], r[1]), make_float2(r[2], r[3])};
             }
         }
     };
 
-    // warm-up of stage 1: the window of a,b row T0 is input rows T0-4 .. T0+3
-    for (int r = T0 - 4; r <= T0 + 2; ++r) feed(r, 1.0);
+    // stage-2 row sums -> q for one output row; i* are the guide channels at the output columns
+    auto emit = [&](unsigned ro, const float4& i0, const float4& i1, const float4& i2) {
+        double h2[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hsum8(S2[q], h2[q]);
+        f2x2 mb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            mb[q] = {make_float2(mean64(h2[q][0]), mean64(h2[q][1])), make_float2(mean64(h2[q][2]), mean64(h2[q][3]))};
+        // q = box(b) + box(a0)*I0 + box(a1)*I1 + box(a2)*I2, accumulated in that order (CVF.cpp:157-163)
+        f2x2 qv = add2(mb[3], mul2(mb[0], from4(i0)));
+        qv = add2(qv, mul2(mb[1], from4(i1)));
+        qv = add2(qv, mul2(mb[2], from4(i2)));
+        if (store_ok) *reinterpret_cast<float4*>(vout + ro) = to4(qv);
+    };
 
-    for (int t = T0; t <= Tend; ++t) {
-        float av[DT][4][4];  // newest a,b row: [slice][plane][column]
+    // ---- generic step: any row, every special case (top weights, warm-up, reflection, virtual rows)
+    auto generic_step = [&](int t) {
         const bool real_row = t <= Tlast;
+        f2x2 av[4];
         if (real_row) {
-            feed(t + 3, 1.0);
-            // ---- stage-1 horizontal sums -> means -> a,b (CVF.cpp:81-155) -------------------
-            const size_t ro = (size_t)t * Wp;
+            const RowIn xn = load_row(t + 3);
+            const RowIn xo = load_row(t - 4);
             float4 g4[10];
-#pragma unroll
-            for (int q = 0; q < 10; ++q) g4[q] = load_row4(G + (size_t)(kGuideMean + q) * plane + ro, ca, W);
-#pragma unroll
-            for (int k = 0; k < DT; ++k) {
-                double h[4][4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) hsum8(S1[k][q], h[q]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    GuidePix g;
-                    g.mI0 = comp(g4[0], j); g.mI1 = comp(g4[1], j); g.mI2 = comp(g4[2], j);
-                    g.M00 = comp(g4[3], j); g.M01 = comp(g4[4], j); g.M02 = comp(g4[5], j);
-                    g.M11 = comp(g4[6], j); g.M12 = comp(g4[7], j); g.M22 = comp(g4[8], j);
-                    g.idet = comp(g4[9], j);
-                    gif_coeffs(mean64(h[0][j]), mean64(h[1][j]), mean64(h[2][j]), mean64(h[3][j]), g,
-                               av[k][0][j], av[k][1][j], av[k][2][j], av[k][3][j]);
-                }
-                if (strip_fix) {  // a,b at columns outside the image := reflected columns (BORDER_REFLECT_101)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float fixed[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float e0 = __shfl_sync(0xffffffffu, av[k][q][0], fix_lane[j]);
-                            const float e1 = __shfl_sync(0xffffffffu, av[k][q][1], fix_lane[j]);
-                            const float e2 = __shfl_sync(0xffffffffu, av[k][q][2], fix_lane[j]);
-                            const float e3 = __shfl_sync(0xffffffffu, av[k][q][3], fix_lane[j]);
-                            const int e = fix_elem[j];
-                            const float v = e == 0 ? e0 : (e == 1 ? e1 : (e == 2 ? e2 : e3));
-                            fixed[j] = fix_need[j] ? v : av[k][q][j];
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) av[k][q][j] = fixed[j];
-                    }
-                }
-            }
-            feed(t - 4, -1.0);  // oldest row of this window leaves before the next a,b row
-        } else {
-            // virtual a,b rows below the image: row t == reflected row 2(H-1)-t, still in the ring
+            load_guide((unsigned)t * Wp, g4);
+            add_row(xn);
+            coeffs(g4, av);
+            sub_row(xo);
+        } else {  // virtual a,b row below the image == reflected row, still in the ring
             const int slot = reflect101(t, H) & 7;
 #pragma unroll
-            for (int k = 0; k < DT; ++k)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 v = ring[((slot * 4 + q) * DT + k) * nthr + tid];
-                    av[k][q][0] = v.x; av[k][q][1] = v.y; av[k][q][2] = v.z; av[k][q][3] = v.w;
-                }
+            for (int q = 0; q < 4; ++q) av[q] = from4(ring[(slot * 4 + q) * nthr + tid]);
         }
-
-        // ---- stage-2 vertical running sums ---------------------------------------------------
-        // window of output row y = t-3 is a,b rows t-7 .. t (reflected at the image top/bottom)
         const int age = t - T0;
         const bool warm = top ? (t <= 4) : (age < 8);
-        const double wnew = (top && t >= 1 && t <= 3) ? 2.0 : 1.0;  // rows 1..3 appear twice in row 0's window
-        const int oslot = (top && t < 8) ? ((8 - t) & 7) : (t & 7);  // slot of row reflect(t-8)
+        const double wnew = (top && t >= 1 && t <= 3) ? 2.0 : 1.0;      // rows 1..3 appear twice in row 0's window
+        const int oslot = (top && t < 8) ? ((8 - t) & 7) : (t & 7);      // slot of a,b row reflect(t-8)
         const int nslot = t & 7;
 #pragma unroll
-        for (int k = 0; k < DT; ++k)
+        for (int q = 0; q < 4; ++q) {
+            float4 old4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!warm) old4 = ring[(oslot * 4 + q) * nthr + tid];
+            if (real_row) ring[(nslot * 4 + q) * nthr + tid] = to4(av[q]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float4 old4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (!warm) old4 = ring[((oslot * 4 + q) * DT + k) * nthr + tid];
-                if (real_row)
-                    ring[((nslot * 4 + q) * DT + k) * nthr + tid] =
-                        make_float4(av[k][q][0], av[k][q][1], av[k][q][2], av[k][q][3]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    double s = __fma_rn(wnew, (double)av[k][q][j], S2[k][q][j]);  // exact: wnew is 1 or 2
-                    if (!warm) s = __dsub_rn(s, (double)comp(old4, j));
-                    S2[k][q][j] = s;
-                }
+            for (int j = 0; j < 4; ++j) {
+                double s = __fma_rn(wnew, (double)get(av[q], j), S2[q][j]);  // exact: wnew is 1 or 2
+                if (!warm) s = __dsub_rn(s, (double)comp(old4, j));
+                S2[q][j] = s;
             }
-
-        // ---- outputs -------------------------------------------------------------------------
+        }
         const bool first_out = top ? (t == 4) : (age == 7);
-        if (warm && !first_out) continue;
-        const int nrows = (top && t == 4) ? 2 : 1;  // rows 0 and 1 share the same reflected window
+        if (warm && !first_out) return;
+        const int nrows = (top && t == 4) ? 2 : 1;  // output rows 0 and 1 share one reflected window
         for (int e = 0; e < nrows; ++e) {
             const int y = (top && t == 4) ? e : t - 3;
             if (y < Y0 || y >= Y1) continue;
-            const size_t ro = (size_t)y * Wp;
-            const float4 i0 = load_row4(G + ro, co, W);
-            const float4 i1 = load_row4(G + plane + ro, co, W);
-            const float4 i2 = load_row4(G + 2 * plane + ro, co, W);
+            const unsigned ro = (unsigned)y * Wp;
+            emit(ro, ldg4(Go + ro), ldg4(Go + plane + ro), ldg4(Go + 2 * plane + ro));
+        }
+    };
+
+    // ---- schedule ----------------------------------------------------------------------------
+    // steady steps need: a real row, no warm-up, no reflected input row (t-4 >= 0, t+4 <= H-1 because
+    // the step also preloads row t+4 for its successor) and the plain ring slot t&7
+    const int Ts0 = top ? 8 : T0 + 8;
+    const int Ts1 = min(Tlast, H - 5);
+
+    for (int r = T0 - 4; r <= T0 + 2; ++r) add_row(load_row(r));
+    int t = T0;
+    for (; t <= Tend && t < Ts0; ++t) generic_step(t);
+
+    if (t <= Ts1) {
+        unsigned ro_n = (unsigned)(t + 3) * Wp;  // newest input row  t+3
+        unsigned ro_o = (unsigned)(t - 4) * Wp;  // oldest input row  t-4
+        unsigned ro_t = (unsigned)t * Wp;        // a,b row           t
+        unsigned ro_y = (unsigned)(t - 3) * Wp;  // output row        t-3
+        RowIn xn = load_at(ro_n);
+        for (; t <= Ts1; ++t) {
+            // every load of this step, and the newest row of the next one, before any math
+            const RowIn xo = load_at(ro_o);
+            float4 g4[10];
+            load_guide(ro_t, g4);
+            const float4 o0 = ldg4(Go + ro_y), o1 = ldg4(Go + plane + ro_y), o2 = ldg4(Go + 2 * plane + ro_y);
+            ro_n += Wp;
+            const RowIn xnext = load_at(ro_n);
+
+            add_row(xn);
+            f2x2 av[4];
+            coeffs(g4, av);
+            sub_row(xo);
+
+            float4* rp = ring + ((t & 7) * 4) * nthr + tid;
 #pragma unroll
-            for (int k = 0; k < DT; ++k) {
-                double h[4][4];
+            for (int q = 0; q < 4; ++q) {
+                const float4 old4 = rp[q * nthr];
+                rp[q * nthr] = to4(av[q]);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) hsum8(S2[k][q], h[q]);
-                float4 q4;
-                float* qp = reinterpret_cast<float*>(&q4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    // q = box(b) + box(a0)*I0 + box(a1)*I1 + box(a2)*I2, accumulated in that order (CVF.cpp:157-163)
-                    float q = mean64(h[3][j]);
-                    q = fadd(q, fmul(mean64(h[0][j]), comp(i0, j)));
-                    q = fadd(q, fmul(mean64(h[1][j]), comp(i1, j)));
-                    q = fadd(q, fmul(mean64(h[2][j]), comp(i2, j)));
-                    qp[j] = q;
-                }
-                if (lane <= 27 && co < W && co >= out_lo && dvalid[k])
-                    *reinterpret_cast<float4*>(vout + (size_t)dl[k] * plane + ro + co) = q4;
+                for (int j = 0; j < 4; ++j)
+                    S2[q][j] = __dsub_rn(__dadd_rn(S2[q][j], (double)get(av[q], j)), (double)comp(old4, j));
             }
+            emit(ro_y, o0, o1, o2);
+
+            xn = xnext;
+            ro_o += Wp; ro_t += Wp; ro_y += Wp;
         }
     }
+    for (; t <= Tend; ++t) generic_step(t);
 }
 
 }  // namespace psm

@@ -1,11 +1,43 @@
 // psm_kernels.cuh -- ingest, cost-volume construction (CVC), guide precompute, WTA and the
 // unfused "naive" CVF cross-check kernels.  The fused streaming CVF kernel is in
-// psm_cvf_stream.cuh.  All layouts: planes are [H][Wp] float (Wp = W rounded up to 4, so every
-// row is 16-byte aligned); volumes are [d_local][H][Wp] float.
+// psm_cvf_stream.cuh.  Layout: every plane / volume row has pitch Wp floats and is stored with a
+// column halo: kPadLeft columns before column 0 and at least kPadRight after column W-1 (so a
+// pointer to (row, col 0) may be indexed from -kPadLeft .. W+kPadRight-1); pitch and halo are
+// multiples of 4 floats, so 4-column groups are 16-byte aligned.  The halos of the cost volumes
+// and of the three guide channels hold the BORDER_REFLECT_101 mirror of the row (written by
+// pad_cols_kernel), which lets the streaming CVF kernel use plain 128-bit loads everywhere.
+// Planes are [H][Wp], volumes [d_local][H][Wp]; "W4" below is W rounded up to 4.
 #pragma once
 #include "psm_common.cuh"
 
 namespace psm {
+
+constexpr int kPadLeft = 8;    // halo columns before column 0
+constexpr int kPadRight = 12;  // minimum halo columns after column W4-1 (the last strip reads up to W+10)
+
+// Row pitch (floats) for an image of width W: left halo + max(W4 + right halo, one full strip).
+__host__ __device__ inline int pitch_for_width(int W)
+{
+    const int w4 = (W + 3) & ~3;
+    const int right = (w4 + kPadRight > 120) ? w4 + kPadRight : 120;
+    return kPadLeft + right;
+}
+
+// Fill the column halos of `nrows` rows with the BORDER_REFLECT_101 mirror of the row:
+// row[-k] = row[k] (k = 1..8), row[W+k] = row[W-2-k] (k = 0..7), zeros beyond.
+__global__ void pad_cols_kernel(float* __restrict__ base, size_t nrows, int W, int Wp)
+{
+    const size_t row = (size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    float* r = base + row * (size_t)Wp;
+    const int lane = threadIdx.x & 31;
+    const int right = Wp - kPadLeft - W;  // halo columns after W-1
+    for (int k = lane; k < kPadLeft + right; k += 32) {
+        const int x = k < kPadLeft ? -(k + 1) : W + (k - kPadLeft);
+        const bool mirrored = x < 0 || x < W + 8;
+        r[x] = mirrored ? r[reflect101(x, W)] : 0.f;
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // Ingest: interleaved BGR (float or u8) -> 3 planar channels + x-gradient of the gray image.
@@ -30,7 +62,7 @@ __global__ void ingest_kernel(const T* __restrict__ src, size_t step_bytes, int 
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
-    if (x >= Wp || y >= H) return;
+    if (x >= ((W + 3) & ~3) || y >= H) return;
     const size_t o = (size_t)y * Wp + x;
     if (x >= W) { I0[o] = 0.f; I1[o] = 0.f; I2[o] = 0.f; grd[o] = 0.f; return; }
     const T* row = reinterpret_cast<const T*>(reinterpret_cast<const char*>(src) + (size_t)y * step_bytes);
@@ -79,7 +111,7 @@ __global__ void __launch_bounds__(128) cvc_kernel(CvcParams P)
 {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
-    if (x4 >= P.Wp) return;
+    if (x4 >= ((P.W + 3) & ~3)) return;
     const int W = P.W;
     const size_t ro = (size_t)y * P.Wp;
 
@@ -202,7 +234,7 @@ __global__ void guide_finish_kernel(const double* __restrict__ hs, float* __rest
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
-    if (x >= Wp) return;
+    if (x >= ((W + 3) & ~3)) return;
     const size_t o = (size_t)y * Wp + x;
     if (x >= W) {
         for (int k = kGuideMean; k < kGuidePlanes; ++k) guide[k * plane + o] = 0.f;

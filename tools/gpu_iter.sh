@@ -8,6 +8,6 @@ timeout 600 python bench.py --steps 10 --warmup 3 ${BENCH_ARGS} > gpurun_out/ben
 echo "bench exit $?" >> gpurun_out/bench.log
 tail -2 gpurun_out/bench.log | cut -c1-1500
 if [ -n "$NCU" ]; then
-  ncu --set full --clock-control none --import-source on -k regex:cvf_stream -s 2 -c 2 -f -o gpurun_out/cvf_prof \
+  ncu --set full --clock-control none --import-source on -k regex:cvf_stream -s 2 -c 1 -f -o gpurun_out/cvf_prof \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu2.log 2>&1
 fi
