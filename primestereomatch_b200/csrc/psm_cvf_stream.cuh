@@ -90,9 +90,15 @@ __device__ __forceinline__ void hsum8(const double c[4], double h[4])
 
 __device__ __forceinline__ float mean64(double s) { return (float)__dmul_rn(s, 1.0 / 64.0); }
 
-__device__ __forceinline__ float4 ldg4(const float* __restrict__ p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldg4(const char* __restrict__ p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-__global__ void __launch_bounds__(kCvfThreads, 3)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// MINB: resident CTAs per SM the register allocation is sized for (3 -> <=168 regs, 2 -> <=255);
+// SYNC: one CTA barrier per steady row keeps the four slice-warps of a CTA in lockstep so that the
+// guide rows one warp pulls into L1 are still there when its three siblings ask for them.
+template <int MINB, bool SYNC>
+__global__ void __launch_bounds__(kCvfThreads, MINB)
 cvf_stream_kernel(const CvfParams P)
 {
     extern __shared__ float4 ring[];  // [8 slots][4 planes][128 threads]
@@ -105,8 +111,9 @@ cvf_stream_kernel(const CvfParams P)
     const int strip = b % P.nstrips;   b /= P.nstrips;
     const int seg = b % P.nseg;
     const int view = b / P.nseg;
-    const int dlc = dgroup * 4 + warp;
-    if (dlc >= P.Dloc) return;  // warps never synchronise with each other
+    const bool slice_ok = dgroup * 4 + warp < P.Dloc;
+    const int dlc = slice_ok ? dgroup * 4 + warp : P.Dloc - 1;  // surplus warps redo the last slice, stores masked
+    if (!SYNC && !slice_ok) return;
 
     const int W = P.W, H = P.H;
     const unsigned Wp = (unsigned)P.Wp;
@@ -114,12 +121,14 @@ cvf_stream_kernel(const CvfParams P)
     const int out_lo = strip * kStripOut;
     const int X0 = (strip == P.nstrips - 1 && strip > 0) ? ((W - kStripOut + 3) & ~3) : out_lo;
     const int cin = X0 - 8 + 4 * lane;
-    const float* __restrict__ Gi = P.guide[view] + cin;                         // guide, input columns
-    const float* __restrict__ Ga = P.guide[view] + cin + 4;                     // guide, a,b columns
-    const float* __restrict__ Go = P.guide[view] + cin + 8;                     // guide, output columns
-    const float* __restrict__ vin = P.vol_in[view] + (size_t)dlc * plane + cin;
-    float* __restrict__ vout = P.vol_out[view] + (size_t)dlc * plane + cin + 8;
-    const bool store_ok = lane <= 27 && cin + 8 < W && cin + 8 >= out_lo;
+    // per-thread base pointers (bytes); every offset added to them below is warp-uniform
+    const char* __restrict__ Gi = reinterpret_cast<const char*>(P.guide[view] + cin);      // guide, input columns
+    const char* __restrict__ Ga = reinterpret_cast<const char*>(P.guide[view] + cin + 4);  // guide, a,b columns
+    const char* __restrict__ Go = reinterpret_cast<const char*>(P.guide[view] + cin + 8);  // guide, output columns
+    const char* __restrict__ vin = reinterpret_cast<const char*>(P.vol_in[view] + (size_t)dlc * plane + cin);
+    char* __restrict__ vout = reinterpret_cast<char*>(P.vol_out[view] + (size_t)dlc * plane + cin + 8);
+    const size_t planeB = (size_t)plane * 4, rowB = (size_t)Wp * 4;
+    const bool store_ok = slice_ok && lane <= 27 && cin + 8 < W && cin + 8 >= out_lo;
 
     // ---- x-reflection plan for a,b (strips whose a,b columns X0-4 .. X0+115 leave the image) ----
     const bool fix_left = X0 == 0;
@@ -153,15 +162,15 @@ cvf_stream_kernel(const CvfParams P)
         for (int j = 0; j < 4; ++j) { S1[q][j] = 0.0; S2[q][j] = 0.0; }
 
     struct RowIn { float4 p, i0, i1, i2; };
-    auto load_at = [&](unsigned ro) {
+    auto load_at = [&](size_t ro) {  // ro: byte offset of the row
         RowIn x;
         x.p = ldg4(vin + ro);
         x.i0 = ldg4(Gi + ro);
-        x.i1 = ldg4(Gi + plane + ro);
-        x.i2 = ldg4(Gi + 2 * plane + ro);
+        x.i1 = ldg4(Gi + (planeB + ro));
+        x.i2 = ldg4(Gi + (2 * planeB + ro));
         return x;
     };
-    auto load_row = [&](int r) { return load_at((unsigned)reflect101(r, H) * Wp); };
+    auto load_row = [&](int r) { return load_at((size_t)reflect101(r, H) * rowB); };
     auto add_row = [&](const RowIn& x) {
         const f2x2 p = from4(x.p);
         const f2x2 m0 = mul2(from4(x.i0), p), m1 = mul2(from4(x.i1), p), m2 = mul2(from4(x.i2), p);  // CVF.cpp:87
@@ -184,9 +193,9 @@ cvf_stream_kernel(const CvfParams P)
             S1[3][j] = __dsub_rn(S1[3][j], (double)get(m2, j));
         }
     };
-    auto load_guide = [&](unsigned ro, float4 (&g4)[10]) {
+    auto load_guide = [&](size_t ro, float4 (&g4)[10]) {
 #pragma unroll
-        for (int q = 0; q < 10; ++q) g4[q] = ldg4(Ga + (unsigned)(kGuideMean + q) * plane + ro);
+        for (int q = 0; q < 10; ++q) g4[q] = ldg4(Ga + ((size_t)(kGuideMean + q) * planeB + ro));
     };
 
     // stage-1 row sums -> means -> cov -> a,b (CVF.cpp:81-155), then the x-reflection of a,b
@@ -236,7 +245,7 @@ cvf_stream_kernel(const CvfParams P)
     };
 
     // stage-2 row sums -> q for one output row; i* are the guide channels at the output columns
-    auto emit = [&](unsigned ro, const float4& i0, const float4& i1, const float4& i2) {
+    auto emit = [&](size_t ro, const float4& i0, const float4& i1, const float4& i2) {
         double h2[4][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) hsum8(S2[q], h2[q]);
@@ -259,7 +268,7 @@ cvf_stream_kernel(const CvfParams P)
             const RowIn xn = load_row(t + 3);
             const RowIn xo = load_row(t - 4);
             float4 g4[10];
-            load_guide((unsigned)t * Wp, g4);
+            load_guide((size_t)t * rowB, g4);
             add_row(xn);
             coeffs(g4, av);
             sub_row(xo);
@@ -291,8 +300,8 @@ cvf_stream_kernel(const CvfParams P)
         for (int e = 0; e < nrows; ++e) {
             const int y = (top && t == 4) ? e : t - 3;
             if (y < Y0 || y >= Y1) continue;
-            const unsigned ro = (unsigned)y * Wp;
-            emit(ro, ldg4(Go + ro), ldg4(Go + plane + ro), ldg4(Go + 2 * plane + ro));
+            const size_t ro = (size_t)y * rowB;
+            emit(ro, ldg4(Go + ro), ldg4(Go + (planeB + ro)), ldg4(Go + (2 * planeB + ro)));
         }
     };
 
@@ -307,24 +316,27 @@ cvf_stream_kernel(const CvfParams P)
     for (; t <= Tend && t < Ts0; ++t) generic_step(t);
 
     if (t <= Ts1) {
-        unsigned ro_n = (unsigned)(t + 3) * Wp;  // newest input row  t+3
-        unsigned ro_o = (unsigned)(t - 4) * Wp;  // oldest input row  t-4
-        unsigned ro_t = (unsigned)t * Wp;        // a,b row           t
-        unsigned ro_y = (unsigned)(t - 3) * Wp;  // output row        t-3
-        RowIn xn = load_at(ro_n);
+        size_t ro_n = (size_t)(t + 3) * rowB;  // newest input row  t+3   (byte offsets)
+        size_t ro_o = (size_t)(t - 4) * rowB;  // oldest input row  t-4
+        size_t ro_t = (size_t)t * rowB;        // a,b row           t
+        size_t ro_y = (size_t)(t - 3) * rowB;  // output row        t-3
+        RowIn xn = load_at(ro_n);   // newest row of this step  (loaded one step ahead)
+        RowIn xo = load_at(ro_o);   // oldest row of this step  (loaded one step ahead)
         for (; t <= Ts1; ++t) {
-            // every load of this step, and the newest row of the next one, before any math
-            const RowIn xo = load_at(ro_o);
+            if (SYNC) __syncthreads();
             float4 g4[10];
             load_guide(ro_t, g4);
-            const float4 o0 = ldg4(Go + ro_y), o1 = ldg4(Go + plane + ro_y), o2 = ldg4(Go + 2 * plane + ro_y);
-            ro_n += Wp;
-            const RowIn xnext = load_at(ro_n);
+            const float4 o0 = ldg4(Go + ro_y), o1 = ldg4(Go + (planeB + ro_y)), o2 = ldg4(Go + (2 * planeB + ro_y));
 
             add_row(xn);
+            ro_n += rowB;
+            xn = load_at(ro_n);     // row t+4 for the next step, into the registers add_row just released
+
             f2x2 av[4];
             coeffs(g4, av);
             sub_row(xo);
+            ro_o += rowB;
+            xo = load_at(ro_o);     // row t-3 for the next step
 
             float4* rp = ring + ((t & 7) * 4) * nthr + tid;
 #pragma unroll
@@ -336,9 +348,7 @@ cvf_stream_kernel(const CvfParams P)
                     S2[q][j] = __dsub_rn(__dadd_rn(S2[q][j], (double)get(av[q], j)), (double)comp(old4, j));
             }
             emit(ro_y, o0, o1, o2);
-
-            xn = xnext;
-            ro_o += Wp; ro_t += Wp; ro_y += Wp;
+            ro_t += rowB; ro_y += rowB;
         }
     }
     for (; t <= Tend; ++t) generic_step(t);
