@@ -261,3 +261,23 @@ def test_sharded_keys_match_unsharded(scenes, oracle_scene_results):
     finally:
         for de in shards:
             de.close()
+
+
+def test_cpp_dispest_facade_demo(tmp_path, scenes, oracle_scene_results):
+    """The C++ DispEst facade (primestereomatch_b200/host), driven like StereoMatch::compute drives the
+    reference's DispEst, produces the oracle's maps on Teddy."""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "primestereomatch_b200", "host", "dispest_demo")
+    if not os.path.exists(exe):
+        pytest.skip("dispest_demo not built")
+    _, _, l, r = scenes["Teddy"]
+    H, W, _ = l.shape
+    l.tofile(tmp_path / "l.f32"); r.tofile(tmp_path / "r.f32")
+    out = subprocess.run([exe, str(W), str(H), "64", str(tmp_path / "l.f32"), str(tmp_path / "r.f32"),
+                          str(tmp_path / "l.u8"), str(tmp_path / "r.u8")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    ld = np.fromfile(tmp_path / "l.u8", np.uint8).reshape(H, W)
+    rd = np.fromfile(tmp_path / "r.u8", np.uint8).reshape(H, W)
+    assert_same(ld, oracle_scene_results["Teddy"]["ld"], "C++ facade lDisMap")
+    assert_same(rd, oracle_scene_results["Teddy"]["rd"], "C++ facade rDisMap")
