@@ -32,7 +32,6 @@ struct psm_ctx {
     float* grd[2] = {nullptr, nullptr};
     float* vol[2] = {nullptr, nullptr};     // current volumes (raw after CVC, filtered after CVF)
     float* vol_alt[2] = {nullptr, nullptr}; // the other half of the ping-pong
-    double* hs = nullptr;                   // guide precompute scratch [9][H][W] fp64
     void* stage_in[2] = {nullptr, nullptr}; // device staging for the interleaved upload
     uint8_t* dis[2] = {nullptr, nullptr};
     float* alloc[16] = {};                  // raw cudaMalloc pointers behind the halo-offset pointers above
@@ -134,10 +133,8 @@ int ensure_guide(psm_ctx* c)
 {
     if (c->guide_valid) return PSM_OK;
     for (int v = 0; v < 2; ++v) {
-        dim3 blk(128), g1((c->W + 127) / 128, c->H), g2((c->W + 3 + 127) / 128, c->H);
-        guide_hsum_kernel<<<g1, blk, 0, c->stream>>>(c->guide[v], c->plane, c->W, c->H, c->Wp, c->hs);
-        PSM_LAUNCH_CHECK(c);
-        guide_finish_kernel<<<g2, blk, 0, c->stream>>>(c->hs, c->guide[v], c->plane, c->W, c->H, c->Wp);
+        dim3 blk(128), grd((c->W + 3 + 127) / 128, (c->H + kGuideSegRows - 1) / kGuideSegRows);
+        guide_kernel<<<grd, blk, 0, c->stream>>>(c->guide[v], c->plane, c->W, c->H, c->Wp);
         PSM_LAUNCH_CHECK(c);
     }
     c->guide_valid = true;
@@ -282,7 +279,6 @@ int psm_create_sharded(psm_ctx** out, int width, int height, int max_disp, int d
         PSM_CREATE_CUDA(cudaMalloc(&c->dis[v], (size_t)c->W * c->H));
         PSM_CREATE_CUDA(cudaMemsetAsync(c->dis[v], 0, (size_t)c->W * c->H, c->stream));
     }
-    PSM_CREATE_CUDA(cudaMalloc(&c->hs, (size_t)9 * c->W * c->H * sizeof(double)));
     for (int s = 0; s < kNumStages; ++s) {
         PSM_CREATE_CUDA(cudaEventCreate(&c->ev0[s]));
         PSM_CREATE_CUDA(cudaEventCreate(&c->ev1[s]));
@@ -305,7 +301,6 @@ int psm_destroy(psm_ctx* c)
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     for (int i = 0; i < c->nalloc; ++i) cudaFree(c->alloc[i]);
     for (int v = 0; v < 2; ++v) { cudaFree(c->stage_in[v]); cudaFree(c->dis[v]); }
-    cudaFree(c->hs);
     cudaFree(c->ab);
     for (int s = 0; s < kNumStages; ++s) {
         if (c->ev0[s]) cudaEventDestroy(c->ev0[s]);
@@ -388,11 +383,13 @@ int psm_cost_const(psm_ctx* c)
         P.other[3] = c->grd[1 - v];
         P.vol = c->vol[v];
         P.W = c->W; P.H = c->H; P.Wp = c->Wp; P.d_begin = c->d_begin; P.d_count = c->d_count;
+        P.fold_halo = c->W >= 32 ? 1 : 0;
         dim3 blk(128), grd((((c->W + 3) / 4) + 127) / 128, c->H);
         if (v == PSM_LEFT) cvc_kernel<-1><<<grd, blk, 0, c->stream>>>(P);
         else cvc_kernel<+1><<<grd, blk, 0, c->stream>>>(P);
         PSM_LAUNCH_CHECK(c);
-        if (int rc = pad_rows(c, c->vol[v], (size_t)c->d_count * c->H)) return rc;  // mirrored halo of every slice row
+        if (!P.fold_halo)  // narrow images: separate halo pass (general reflection)
+            if (int rc = pad_rows(c, c->vol[v], (size_t)c->d_count * c->H)) return rc;
     }
     c->have_cvc = true;
     return stage_end(c, 1);

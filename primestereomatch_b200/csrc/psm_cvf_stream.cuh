@@ -95,9 +95,8 @@ __device__ __forceinline__ float4 ldg4(const char* __restrict__ p) { return __ld
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // MINB: resident CTAs per SM the register allocation is sized for (3 -> <=168 regs, 2 -> <=255);
-// SYNC: one CTA barrier per steady row keeps the four slice-warps of a CTA in lockstep so that the
-// guide rows one warp pulls into L1 are still there when its three siblings ask for them.
-template <int MINB, bool SYNC>
+// SKEW: run stage 2 of row t-1 next to stage 1 of row t in the steady loop (two independent streams).
+template <int MINB, bool SKEW>
 __global__ void __launch_bounds__(kCvfThreads, MINB)
 cvf_stream_kernel(const CvfParams P)
 {
@@ -113,7 +112,7 @@ cvf_stream_kernel(const CvfParams P)
     const int view = b / P.nseg;
     const bool slice_ok = dgroup * 4 + warp < P.Dloc;
     const int dlc = slice_ok ? dgroup * 4 + warp : P.Dloc - 1;  // surplus warps redo the last slice, stores masked
-    if (!SYNC && !slice_ok) return;
+    if (!slice_ok) return;  // warps never synchronise with each other
 
     const int W = P.W, H = P.H;
     const unsigned Wp = (unsigned)P.Wp;
@@ -320,25 +319,24 @@ cvf_stream_kernel(const CvfParams P)
         size_t ro_o = (size_t)(t - 4) * rowB;  // oldest input row  t-4
         size_t ro_t = (size_t)t * rowB;        // a,b row           t
         size_t ro_y = (size_t)(t - 3) * rowB;  // output row        t-3
-        RowIn xn = load_at(ro_n);   // newest row of this step  (loaded one step ahead)
-        RowIn xo = load_at(ro_o);   // oldest row of this step  (loaded one step ahead)
-        for (; t <= Ts1; ++t) {
-            if (SYNC) __syncthreads();
+        RowIn xn = load_at(ro_n);   // newest row of the next stage-1 step (loaded one step ahead)
+        RowIn xo = load_at(ro_o);   // oldest row of the next stage-1 step (loaded one step ahead)
+        // stage 1 of a,b row ro_t: S1 += newest, row sums -> a,b, S1 -= oldest; refills xn / xo
+        auto stage1 = [&](f2x2 (&av)[4]) {
             float4 g4[10];
             load_guide(ro_t, g4);
-            const float4 o0 = ldg4(Go + ro_y), o1 = ldg4(Go + (planeB + ro_y)), o2 = ldg4(Go + (2 * planeB + ro_y));
-
             add_row(xn);
             ro_n += rowB;
-            xn = load_at(ro_n);     // row t+4 for the next step, into the registers add_row just released
-
-            f2x2 av[4];
+            xn = load_at(ro_n);     // into the registers add_row just released
             coeffs(g4, av);
             sub_row(xo);
             ro_o += rowB;
-            xo = load_at(ro_o);     // row t-3 for the next step
-
-            float4* rp = ring + ((t & 7) * 4) * nthr + tid;
+            xo = load_at(ro_o);
+            ro_t += rowB;
+        };
+        // stage 2 of a,b row tt (output row tt-3 at byte offset ro_y): ring exchange, S2 update, q
+        auto stage2 = [&](int tt, const f2x2 (&av)[4], const float4& o0, const float4& o1, const float4& o2) {
+            float4* rp = ring + ((tt & 7) * 4) * nthr + tid;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 old4 = rp[q * nthr];
@@ -348,7 +346,31 @@ cvf_stream_kernel(const CvfParams P)
                     S2[q][j] = __dsub_rn(__dadd_rn(S2[q][j], (double)get(av[q], j)), (double)comp(old4, j));
             }
             emit(ro_y, o0, o1, o2);
-            ro_t += rowB; ro_y += rowB;
+            ro_y += rowB;
+        };
+        if (!SKEW) {
+            for (; t <= Ts1; ++t) {
+                const float4 o0 = ldg4(Go + ro_y), o1 = ldg4(Go + (planeB + ro_y)), o2 = ldg4(Go + (2 * planeB + ro_y));
+                f2x2 av[4];
+                stage1(av);
+                stage2(t, av, o0, o1, o2);
+            }
+        } else {
+            // software-skewed: stage 2 of row t-1 and stage 1 of row t are independent instruction
+            // streams inside one loop body, so each hides the other's pipe latencies
+            f2x2 avp[4];
+            stage1(avp);
+            int tp = t++;
+            for (; t <= Ts1; ++t) {
+                const float4 o0 = ldg4(Go + ro_y), o1 = ldg4(Go + (planeB + ro_y)), o2 = ldg4(Go + (2 * planeB + ro_y));
+                f2x2 avc[4];
+                stage1(avc);
+                stage2(tp, avp, o0, o1, o2);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) avp[q] = avc[q];
+                tp = t;
+            }
+            stage2(tp, avp, ldg4(Go + ro_y), ldg4(Go + (planeB + ro_y)), ldg4(Go + (2 * planeB + ro_y)));
         }
     }
     for (; t <= Tend; ++t) generic_step(t);

@@ -12,15 +12,17 @@
 
 namespace psm {
 
-constexpr int kPadLeft = 8;    // halo columns before column 0
+constexpr int kPadLeft = 32;   // floats before column 0 (128 B: column 0 of every row is cache-line aligned);
+                               // the last 8 of them are the mirrored left halo
 constexpr int kPadRight = 12;  // minimum halo columns after column W4-1 (the last strip reads up to W+10)
 
-// Row pitch (floats) for an image of width W: left halo + max(W4 + right halo, one full strip).
+// Row pitch (floats) for an image of width W: left pad + max(W4 + right halo, one full strip),
+// rounded up to a multiple of 32 floats so that every row starts on a 128-byte line.
 __host__ __device__ inline int pitch_for_width(int W)
 {
     const int w4 = (W + 3) & ~3;
     const int right = (w4 + kPadRight > 120) ? w4 + kPadRight : 120;
-    return kPadLeft + right;
+    return kPadLeft + ((right + 31) & ~31);
 }
 
 // Fill the column halos of `nrows` rows with the BORDER_REFLECT_101 mirror of the row:
@@ -34,7 +36,7 @@ __global__ void pad_cols_kernel(float* __restrict__ base, size_t nrows, int W, i
     const int right = Wp - kPadLeft - W;  // halo columns after W-1
     for (int k = lane; k < kPadLeft + right; k += 32) {
         const int x = k < kPadLeft ? -(k + 1) : W + (k - kPadLeft);
-        const bool mirrored = x < 0 || x < W + 8;
+        const bool mirrored = (x < 0 && x >= -8) || (x >= W && x < W + 8);
         r[x] = mirrored ? r[reflect101(x, W)] : 0.f;
     }
 }
@@ -87,6 +89,7 @@ struct CvcParams {
     const float* other[4];  // planes of the matched view
     float* vol;             // [d_count][H][Wp]
     int W, H, Wp, d_begin, d_count;
+    int fold_halo;          // 1: this kernel also writes the mirrored column halo (W >= 32)
 };
 
 __device__ __forceinline__ float cost4(float l0, float l1, float l2, float lg,
@@ -140,6 +143,21 @@ __global__ void __launch_bounds__(128) cvc_kernel(CvcParams P)
     }
     const size_t slice = (size_t)P.H * P.Wp;
     float* out = P.vol + ro + x4;
+    // mirrored column halo (see pad_cols_kernel), written here for W >= 32: pixel x in [1,8] also goes to
+    // column -x, pixel x in [W-9, W-2] also to column 2(W-1)-x.  Only the edge threads of a row take part.
+    int halo_off[4];
+    bool edge = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = x4 + j;
+        halo_off[j] = 0;
+        if (P.fold_halo && x < W) {
+            if (x >= 1 && x <= 8) halo_off[j] = -x - x4;
+            else if (x >= W - 9 && x <= W - 2) halo_off[j] = 2 * (W - 1) - x - x4;
+        }
+        edge |= halo_off[j] != 0;
+    }
+    const bool full_group = x4 + 3 < W || !P.fold_halo;
 #pragma unroll 4
     for (int dl = 0; dl < P.d_count; ++dl, ++d) {
         float4 r;
@@ -151,7 +169,16 @@ __global__ void __launch_bounds__(128) cvc_kernel(CvcParams P)
             const float c = cost4(s[0][j], s[1][j], s[2][j], s[3][j], w[0][j], w[1][j], w[2][j], w[3][j]);
             rp[j] = (x < W) ? (interior ? c : bord[j]) : 0.f;
         }
-        *reinterpret_cast<float4*>(out + (size_t)dl * slice) = r;
+        float* o = out + (size_t)dl * slice;
+        if (full_group) *reinterpret_cast<float4*>(o) = r;
+        else {  // last, partial group of a row: columns >= W belong to the mirrored halo
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (x4 + j < W) o[j] = rp[j];
+        }
+        if (edge) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (halo_off[j] != 0) o[halo_off[j]] = rp[j];
+        }
         // slide the window by one disparity
         if (SIGN < 0) {
             const int xo = clampx(x4 - (d + 1));
@@ -191,29 +218,25 @@ __device__ __forceinline__ float box8_direct(F tap, int x, int y, int W, int H)
 // ------------------------------------------------------------------------------------------
 // K2 guide precompute (CVF::preprocess, CVF.cpp:44-70) + the d-independent part of the 3x3
 // solve of GuidedFilter_cv (CVF.cpp:117-126): the symmetric adjugate of (Sigma + eps I) and
-// 1/det.  Separable: pass H writes fp64 horizontal 8-sums of the 9 planes
-// (I_c, I_c*I_c'), pass V finishes the box, forms mean/var and the solve terms.
+// 1/det.  One fused kernel: fp64 horizontal 8-sums of the 9 planes (I_c, I_c*I_c') per row,
+// fp64 running sums down the rows of a segment, then mean/var and the solve terms.
 // guide planes (each [H][Wp]): 0-2 I, 3-5 mean_I, 6-11 adj (M00,M01,M02,M11,M12,M22), 12 1/det,
 // 13-18 var_I (rr,rg,rb,gg,gb,bb; kept for parity reads).
 // ------------------------------------------------------------------------------------------
 constexpr int kGuideI = 0, kGuideMean = 3, kGuideAdj = 6, kGuideIdet = 12, kGuideVar = 13, kGuidePlanes = 19;
 
-__global__ void guide_hsum_kernel(const float* __restrict__ guide, size_t plane, int W, int H, int Wp,
-                                  double* __restrict__ hs /* [9][H][W] */)
+// One thread = one column of one row segment.  Horizontal taps x-4 .. x+3 come straight from the
+// mirrored column halo of the I planes (pad_cols_kernel has run); rows reflect by index.
+__device__ __forceinline__ void guide_row_sums(const float* __restrict__ I0, size_t plane, size_t ro, int x, double s[9])
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    if (x >= W) return;
-    const float* I0 = guide + (size_t)y * Wp;
-    const float* I1 = I0 + plane;
-    const float* I2 = I1 + plane;
-    double s[9];
+    const float* p0 = I0 + ro + x;
+    const float* p1 = p0 + plane;
+    const float* p2 = p1 + plane;
 #pragma unroll
     for (int k = 0; k < 9; ++k) s[k] = 0.0;
 #pragma unroll
     for (int dx = -kBoxAnchor; dx < kBoxK - kBoxAnchor; ++dx) {
-        const int xx = reflect101(x + dx, W);
-        const float a = __ldg(I0 + xx), b = __ldg(I1 + xx), c = __ldg(I2 + xx);
+        const float a = __ldg(p0 + dx), b = __ldg(p1 + dx), c = __ldg(p2 + dx);
         s[0] = __dadd_rn(s[0], (double)a);
         s[1] = __dadd_rn(s[1], (double)b);
         s[2] = __dadd_rn(s[2], (double)c);
@@ -224,69 +247,76 @@ __global__ void guide_hsum_kernel(const float* __restrict__ guide, size_t plane,
         s[7] = __dadd_rn(s[7], (double)fmul(b, c));  // gb
         s[8] = __dadd_rn(s[8], (double)fmul(c, c));  // bb
     }
-    const size_t hp = (size_t)H * W;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) hs[k * hp + (size_t)y * W + x] = s[k];
 }
 
-__global__ void guide_finish_kernel(const double* __restrict__ hs, float* __restrict__ guide, size_t plane,
-                                    int W, int H, int Wp)
+constexpr int kGuideSegRows = 32;
+
+__global__ void __launch_bounds__(128) guide_kernel(float* __restrict__ guide, size_t plane, int W, int H, int Wp)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
     if (x >= ((W + 3) & ~3)) return;
-    const size_t o = (size_t)y * Wp + x;
+    const int y0 = blockIdx.y * kGuideSegRows;
+    const int y1 = min(H, y0 + kGuideSegRows);
     if (x >= W) {
-        for (int k = kGuideMean; k < kGuidePlanes; ++k) guide[k * plane + o] = 0.f;
+        for (int y = y0; y < y1; ++y)
+            for (int k = kGuideMean; k < kGuidePlanes; ++k) guide[k * plane + (size_t)y * Wp + x] = 0.f;
         return;
     }
-    const size_t hp = (size_t)H * W;
-    float m[9];
+    double V[9], s[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        double s = 0.0;
+    for (int k = 0; k < 9; ++k) V[k] = 0.0;
+    for (int r = y0 - kBoxAnchor; r < y0 + kBoxK - kBoxAnchor - 1; ++r) {
+        guide_row_sums(guide, plane, (size_t)reflect101(r, H) * Wp, x, s);
 #pragma unroll
-        for (int dy = -kBoxAnchor; dy < kBoxK - kBoxAnchor; ++dy)
-            s = __dadd_rn(s, hs[k * hp + (size_t)reflect101(y + dy, H) * W + x]);
-        m[k] = (float)__dmul_rn(s, 1.0 / 64.0);
+        for (int k = 0; k < 9; ++k) V[k] = __dadd_rn(V[k], s[k]);
     }
-    // var_I[idx] = box(I_c * I_c') - mean_c * mean_c'   (CVF.cpp:60-69)
-    float v[6];
-    v[0] = fsub(m[3], fmul(m[0], m[0]));
-    v[1] = fsub(m[4], fmul(m[0], m[1]));
-    v[2] = fsub(m[5], fmul(m[0], m[2]));
-    v[3] = fsub(m[6], fmul(m[1], m[1]));
-    v[4] = fsub(m[7], fmul(m[1], m[2]));
-    v[5] = fsub(m[8], fmul(m[2], m[2]));
-    // CVF.cpp:108-116
-    const float a11 = fadd(v[0], kGifEps), a12 = v[1], a13 = v[2];
-    const float a21 = v[1], a22 = fadd(v[3], kGifEps), a23 = v[4];
-    const float a31 = v[2], a32 = v[4], a33 = fadd(v[5], kGifEps);
-    // cofactors exactly as written at CVF.cpp:117-146 (the adjugate is symmetric bit-for-bit
-    // because each mirrored entry is the same two products in commuted order)
-    const float M00 = fsub(fmul(a33, a22), fmul(a32, a23));
-    const float M01 = fsub(fmul(a31, a23), fmul(a33, a21));
-    const float M02 = fsub(fmul(a32, a21), fmul(a31, a22));
-    const float M11 = fsub(fmul(a33, a11), fmul(a31, a13));
-    const float M12 = fsub(fmul(a31, a12), fmul(a32, a11));
-    const float M22 = fsub(fmul(a22, a11), fmul(a21, a12));
-    // DET = a11*(a33*a22-a32*a23) - a21*(a33*a12-a32*a13) + a31*(a23*a12-a22*a13)  (CVF.cpp:117-119)
-    const float t1 = fsub(fmul(a33, a12), fmul(a32, a13));
-    const float t2 = fsub(fmul(a23, a12), fmul(a22, a13));
-    float det = fadd(fsub(fmul(a11, M00), fmul(a21, t1)), fmul(a31, t2));
-    det = __fdiv_rn(1.0f, det);  // CVF.cpp:120
-    guide[(kGuideMean + 0) * plane + o] = m[0];
-    guide[(kGuideMean + 1) * plane + o] = m[1];
-    guide[(kGuideMean + 2) * plane + o] = m[2];
-    guide[(kGuideAdj + 0) * plane + o] = M00;
-    guide[(kGuideAdj + 1) * plane + o] = M01;
-    guide[(kGuideAdj + 2) * plane + o] = M02;
-    guide[(kGuideAdj + 3) * plane + o] = M11;
-    guide[(kGuideAdj + 4) * plane + o] = M12;
-    guide[(kGuideAdj + 5) * plane + o] = M22;
-    guide[kGuideIdet * plane + o] = det;
+    for (int y = y0; y < y1; ++y) {
+        guide_row_sums(guide, plane, (size_t)reflect101(y + kBoxK - kBoxAnchor - 1, H) * Wp, x, s);
+        float m[9];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) guide[(kGuideVar + k) * plane + o] = v[k];
+        for (int k = 0; k < 9; ++k) { V[k] = __dadd_rn(V[k], s[k]); m[k] = (float)__dmul_rn(V[k], 1.0 / 64.0); }
+        guide_row_sums(guide, plane, (size_t)reflect101(y - kBoxAnchor, H) * Wp, x, s);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) V[k] = __dsub_rn(V[k], s[k]);
+        const size_t o = (size_t)y * Wp + x;
+        // var_I[idx] = box(I_c * I_c') - mean_c * mean_c'   (CVF.cpp:60-69)
+        float v[6];
+        v[0] = fsub(m[3], fmul(m[0], m[0]));
+        v[1] = fsub(m[4], fmul(m[0], m[1]));
+        v[2] = fsub(m[5], fmul(m[0], m[2]));
+        v[3] = fsub(m[6], fmul(m[1], m[1]));
+        v[4] = fsub(m[7], fmul(m[1], m[2]));
+        v[5] = fsub(m[8], fmul(m[2], m[2]));
+        // CVF.cpp:108-116
+        const float a11 = fadd(v[0], kGifEps), a12 = v[1], a13 = v[2];
+        const float a21 = v[1], a22 = fadd(v[3], kGifEps), a23 = v[4];
+        const float a31 = v[2], a32 = v[4], a33 = fadd(v[5], kGifEps);
+        // cofactors exactly as written at CVF.cpp:117-146 (the adjugate is symmetric bit-for-bit
+        // because each mirrored entry is the same two products in commuted order)
+        const float M00 = fsub(fmul(a33, a22), fmul(a32, a23));
+        const float M01 = fsub(fmul(a31, a23), fmul(a33, a21));
+        const float M02 = fsub(fmul(a32, a21), fmul(a31, a22));
+        const float M11 = fsub(fmul(a33, a11), fmul(a31, a13));
+        const float M12 = fsub(fmul(a31, a12), fmul(a32, a11));
+        const float M22 = fsub(fmul(a22, a11), fmul(a21, a12));
+        // DET = a11*(a33*a22-a32*a23) - a21*(a33*a12-a32*a13) + a31*(a23*a12-a22*a13)  (CVF.cpp:117-119)
+        const float t1 = fsub(fmul(a33, a12), fmul(a32, a13));
+        const float t2 = fsub(fmul(a23, a12), fmul(a22, a13));
+        float det = fadd(fsub(fmul(a11, M00), fmul(a21, t1)), fmul(a31, t2));
+        det = __fdiv_rn(1.0f, det);  // CVF.cpp:120
+        guide[(kGuideMean + 0) * plane + o] = m[0];
+        guide[(kGuideMean + 1) * plane + o] = m[1];
+        guide[(kGuideMean + 2) * plane + o] = m[2];
+        guide[(kGuideAdj + 0) * plane + o] = M00;
+        guide[(kGuideAdj + 1) * plane + o] = M01;
+        guide[(kGuideAdj + 2) * plane + o] = M02;
+        guide[(kGuideAdj + 3) * plane + o] = M11;
+        guide[(kGuideAdj + 4) * plane + o] = M12;
+        guide[(kGuideAdj + 5) * plane + o] = M22;
+        guide[kGuideIdet * plane + o] = det;
+    #pragma unroll
+        for (int k = 0; k < 6; ++k) guide[(kGuideVar + k) * plane + o] = v[k];
+    }
 }
 
 // Per-voxel coefficient math shared by every CVF kernel: CVF.cpp:92-95 (cov), :121-146 (a),
