@@ -252,7 +252,7 @@ def main():
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "cvf_traffic.json")
-        if os.path.exists(tp):
+        if world == 1 and os.path.exists(tp):
             try:
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
