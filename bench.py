@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--cvf-mode", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seg-rows", type=int, default=0)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -175,6 +176,7 @@ def main():
     de = DispEst(l, r, D, 8, True, device=local_rank, d_begin=d_begin, d_count=d_count)
     de.set_option(capi.PSM_OPT_CVF_MODE, args.cvf_mode)
     de.set_option(capi.PSM_OPT_VARIANT, args.variant)
+    de.set_option(101, args.seg_rows)
     stream = torch.cuda.Stream()  # a real (non-default) stream: handle 0 would mean "context's own stream"
     torch.cuda.set_stream(stream)
     capi.check(L.psm_set_stream(de.handle, C.c_void_p(stream.cuda_stream)), de.handle)
