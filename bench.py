@@ -140,6 +140,9 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seg-rows", type=int, default=0)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: p2p = WTA kernel stores its minima into every rank's buffer over NVLink (fused "
+                         "compute+exchange); nccl = local WTA then ncclAllGather")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -184,9 +187,13 @@ def main():
     npix = W * H
     lmap = torch.empty((H, W), dtype=torch.uint8).pin_memory()
     rmap = torch.empty((H, W), dtype=torch.uint8).pin_memory()
-    if world > 1:
+    p2p = None
+    if world > 1 and args.exchange == "nccl":
         keys = torch.empty((2, npix), dtype=torch.int64, device="cuda")
         gathered = torch.empty((2, world, npix), dtype=torch.int64, device="cuda")
+    elif world > 1:
+        from primestereomatch_b200.sharding import P2PExchange
+        p2p = P2PExchange(de, world, rank)
     step_bytes = W * 3 * 4
 
     def step(e2e):
@@ -201,6 +208,10 @@ def main():
                 capi.check(L.psm_disp_select(de.handle, lmap.data_ptr(), W, rmap.data_ptr(), W), de.handle)
             else:
                 capi.check(L.psm_disp_select_device(de.handle), de.handle)
+        elif p2p is not None:
+            p2p.select()    # WTA + all-gather in one kernel (peer stores)
+            p2p.barrier()
+            p2p.reduce(lmap.data_ptr() if e2e else None, rmap.data_ptr() if e2e else None)
         else:
             capi.check(L.psm_disp_select_keys(de.handle, keys[0].data_ptr(), keys[1].data_ptr()), de.handle)
             dist.all_gather_into_tensor(gathered[0].view(-1), keys[0])
@@ -263,7 +274,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": f"disparity-sharded x{world}" if world > 1 else "single GPU",
+            "config": {"workload": WORKLOAD, "parallelism": (f"disparity-sharded x{world}, exchange={args.exchange}") if world > 1 else "single GPU",
                        "cvf_mode": ["exact", "mixed", "naive"][args.cvf_mode], "variant": args.variant,
                        "l2": "inputs larger than L2: each step streams 4 x 1.06 GB volumes (raw+filtered, 2 views), no flush needed",
                        "stage_ms_last_step": stage},

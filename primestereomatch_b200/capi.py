@@ -15,7 +15,8 @@ SYMBOLS = [
     "psm_device_count", "psm_create", "psm_create_sharded", "psm_destroy", "psm_set_option",
     "psm_set_stream", "psm_set_images", "psm_set_images_u8", "psm_set_images_device",
     "psm_cost_const", "psm_cost_filter", "psm_disp_select", "psm_disp_select_device",
-    "psm_disp_select_keys", "psm_disp_reduce_keys", "psm_read_cost_slice", "psm_write_cost_slice",
+    "psm_disp_select_keys", "psm_disp_reduce_keys", "psm_p2p_create_buffer", "psm_ipc_export", "psm_ipc_import",
+    "psm_p2p_set_peers", "psm_disp_select_keys_p2p", "psm_disp_reduce_p2p", "psm_read_cost_slice", "psm_write_cost_slice",
     "psm_read_guide_plane", "psm_read_ab_slice", "psm_device_ptr", "psm_stage_ms",
     "psm_launch_count", "psm_sync", "psm_last_error", "psm_build_info",
 ]
@@ -60,6 +61,12 @@ def lib():
     L.psm_disp_select_device.argtypes = [vp]
     L.psm_disp_select_keys.argtypes = [vp, vp, vp]
     L.psm_disp_reduce_keys.argtypes = [vp, vp, vp, i, u8p, sz, u8p, sz]
+    L.psm_p2p_create_buffer.argtypes = [vp, i, C.POINTER(vp)]
+    L.psm_ipc_export.argtypes = [vp, vp, C.c_char_p]
+    L.psm_ipc_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.psm_p2p_set_peers.argtypes = [vp, C.POINTER(vp), i, i]
+    L.psm_disp_select_keys_p2p.argtypes = [vp]
+    L.psm_disp_reduce_p2p.argtypes = [vp, u8p, sz, u8p, sz]
     L.psm_read_cost_slice.argtypes = [vp, i, i, fp, sz]
     L.psm_write_cost_slice.argtypes = [vp, i, i, fp, sz]
     L.psm_read_guide_plane.argtypes = [vp, i, i, fp, sz]

@@ -34,6 +34,10 @@ struct psm_ctx {
     float* vol_alt[2] = {nullptr, nullptr}; // the other half of the ping-pong
     void* stage_in[2] = {nullptr, nullptr}; // device staging for the interleaved upload
     uint8_t* dis[2] = {nullptr, nullptr};
+    unsigned long long* p2p_own = nullptr;  // own gather buffer [2 parity][2 views][nranks][H*W]
+    unsigned long long* p2p_peer[8] = {};   // every rank's gather buffer as mapped here
+    void* p2p_imported[8] = {};             // IPC mappings to close at destroy
+    int p2p_nimported = 0, p2p_nranks = 0, p2p_rank = 0, p2p_parity = 0;
     float* alloc[16] = {};                  // raw cudaMalloc pointers behind the halo-offset pointers above
     int nalloc = 0;
     bool cvf_attr_set = false;
@@ -300,6 +304,8 @@ int psm_destroy(psm_ctx* c)
     if (!c) return PSM_OK;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    for (int i = 0; i < c->p2p_nimported; ++i) cudaIpcCloseMemHandle(c->p2p_imported[i]);
+    cudaFree(c->p2p_own);
     for (int i = 0; i < c->nalloc; ++i) cudaFree(c->alloc[i]);
     for (int v = 0; v < 2; ++v) { cudaFree(c->stage_in[v]); cudaFree(c->dis[v]); }
     cudaFree(c->ab);
@@ -478,6 +484,91 @@ int psm_disp_reduce_keys(psm_ctx* c, const uint64_t* d_gathered_left, const uint
     for (int v = 0; v < 2; ++v) {
         keys_reduce_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, c->stream>>>(
             reinterpret_cast<const unsigned long long*>(g[v]), nranks, npix, c->dis[v]);
+        PSM_LAUNCH_CHECK(c);
+    }
+    if (left && right) {
+        if (int rc = copy_map_out(c, c->dis[0], left, left_step)) return rc;
+        if (int rc = copy_map_out(c, c->dis[1], right, right_step)) return rc;
+    }
+    PSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PSM_OK;
+}
+
+int psm_p2p_create_buffer(psm_ctx* c, int nranks, void** d_buffer)
+{
+    if (int rc = bind(c)) return rc;
+    if (nranks < 1 || nranks > 8 || !d_buffer) return fail(c, PSM_EINVAL, "bad nranks %d (1..8)", nranks);
+    if (c->p2p_own) { cudaFree(c->p2p_own); c->p2p_own = nullptr; }
+    const size_t n = (size_t)4 * nranks * c->W * c->H;
+    PSM_CUDA(c, cudaMalloc(&c->p2p_own, n * sizeof(unsigned long long)));
+    PSM_CUDA(c, cudaMemsetAsync(c->p2p_own, 0xff, n * sizeof(unsigned long long), c->stream));
+    PSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->p2p_nranks = nranks;
+    *d_buffer = c->p2p_own;
+    return PSM_OK;
+}
+
+int psm_ipc_export(psm_ctx* c, void* d_ptr, unsigned char handle_out[64])
+{
+    if (int rc = bind(c)) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    PSM_CUDA(c, cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle_out, &h, 64);
+    return PSM_OK;
+}
+
+int psm_ipc_import(psm_ctx* c, const unsigned char handle[64], void** d_ptr)
+{
+    if (int rc = bind(c)) return rc;
+    if (c->p2p_nimported >= 8) return fail(c, PSM_EINVAL, "too many imported buffers");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    PSM_CUDA(c, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->p2p_imported[c->p2p_nimported++] = *d_ptr;
+    return PSM_OK;
+}
+
+int psm_p2p_set_peers(psm_ctx* c, void* const* d_buffers, int nranks, int rank)
+{
+    if (!c || !d_buffers) return fail(c, PSM_EINVAL, "null argument");
+    if (nranks != c->p2p_nranks || rank < 0 || rank >= nranks) return fail(c, PSM_EINVAL, "bad peers (nranks %d, rank %d)", nranks, rank);
+    for (int r = 0; r < nranks; ++r) {
+        if (!d_buffers[r]) return fail(c, PSM_EINVAL, "null buffer for rank %d", r);
+        c->p2p_peer[r] = static_cast<unsigned long long*>(d_buffers[r]);
+    }
+    c->p2p_rank = rank;
+    c->p2p_parity = 0;
+    return PSM_OK;
+}
+
+int psm_disp_select_keys_p2p(psm_ctx* c)
+{
+    if (int rc = bind(c)) return rc;
+    if (!c->p2p_own || !c->p2p_peer[0]) return fail(c, PSM_ESTATE, "psm_p2p_create_buffer / psm_p2p_set_peers first");
+    if (int rc = stage_begin(c, 3)) return rc;
+    const size_t npix = (size_t)c->W * c->H;
+    c->p2p_parity ^= 1;
+    for (int v = 0; v < 2; ++v) {
+        P2pPeers peers;
+        peers.nranks = c->p2p_nranks; peers.rank = c->p2p_rank;
+        for (int r = 0; r < 8; ++r)
+            peers.buf[r] = r < c->p2p_nranks ? c->p2p_peer[r] + ((size_t)c->p2p_parity * 2 + v) * c->p2p_nranks * npix : nullptr;
+        dim3 blk(256), grd(((c->W + 3) / 4 + 255) / 256, c->H);
+        wta_p2p_kernel<<<grd, blk, 0, c->stream>>>(c->vol[v], c->W, c->H, c->Wp, c->d_begin, c->d_count, peers);
+        PSM_LAUNCH_CHECK(c);
+    }
+    return stage_end(c, 3);
+}
+
+int psm_disp_reduce_p2p(psm_ctx* c, uint8_t* left, size_t left_step, uint8_t* right, size_t right_step)
+{
+    if (int rc = bind(c)) return rc;
+    if (!c->p2p_own) return fail(c, PSM_ESTATE, "no gather buffer");
+    const size_t npix = (size_t)c->W * c->H;
+    for (int v = 0; v < 2; ++v) {
+        const unsigned long long* g = c->p2p_own + ((size_t)c->p2p_parity * 2 + v) * c->p2p_nranks * npix;
+        keys_reduce_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, c->stream>>>(g, c->p2p_nranks, npix, c->dis[v]);
         PSM_LAUNCH_CHECK(c);
     }
     if (left && right) {

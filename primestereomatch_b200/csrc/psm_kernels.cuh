@@ -429,6 +429,51 @@ __global__ void __launch_bounds__(256) wta_kernel(const float* __restrict__ vol,
     }
 }
 
+// WTA fused with the all-gather of the sharded path: the same scan as wta_kernel, but the packed
+// (cost,d) minimum of every pixel is stored into slot `rank` of EVERY rank's gather buffer -- peer
+// device memory mapped over NVLink -- so compute and exchange are one kernel.
+struct P2pPeers {
+    unsigned long long* buf[8];  // gather buffers [nranks][H*W] of this view and frame parity, per rank
+    int nranks, rank;
+};
+
+__global__ void __launch_bounds__(256) wta_p2p_kernel(const float* __restrict__ vol, int W, int H, int Wp, int d_begin, int d_count,
+                                                      P2pPeers peers)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x4 >= W) return;
+    const size_t plane = (size_t)H * Wp;
+    const float* p = vol + (size_t)y * Wp + x4;
+    float mc[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    int md[4] = {0, 0, 0, 0};
+    int dl = (d_begin == 0) ? 1 : 0;
+#pragma unroll 8
+    for (; dl < d_count; ++dl) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(p + (size_t)dl * plane));
+        const int d = d_begin + dl;
+        if (c.x < mc[0]) { mc[0] = c.x; md[0] = d; }
+        if (c.y < mc[1]) { mc[1] = c.y; md[1] = d; }
+        if (c.z < mc[2]) { mc[2] = c.z; md[2] = d; }
+        if (c.w < mc[3]) { mc[3] = c.w; md[3] = d; }
+    }
+    const size_t npix = (size_t)W * H;
+    const size_t base = (size_t)peers.rank * npix + (size_t)y * W + x4;
+    unsigned long long k[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k[j] = ((unsigned long long)float_order_key(mc[j]) << 32) | (unsigned)md[j];
+    for (int r = 0; r < peers.nranks; ++r) {
+        unsigned long long* dst = peers.buf[r] + base;  // peer (or own) memory
+        if (x4 + 3 < W && (((size_t)dst) & 15) == 0) {
+            reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(k[0], k[1]);
+            reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(k[2], k[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (x4 + j < W) dst[j] = k[j];
+        }
+    }
+}
+
 // Final step of the sharded WTA: min over ranks of the packed keys, low 8 bits -> u8 map.
 __global__ void keys_reduce_kernel(const unsigned long long* __restrict__ gathered, int nranks, size_t npix,
                                    uint8_t* __restrict__ dis)

@@ -33,3 +33,47 @@ def gather_and_reduce(de, keys, gathered, world, lmap=None, rmap=None, group=Non
     rp = rmap.ctypes.data_as(C.c_void_p) if rmap is not None else None
     capi.check(L.psm_disp_reduce_keys(de.handle, gathered[0].data_ptr(), gathered[1].data_ptr(), world,
                                       lp, de.wid, rp, de.wid), de.handle)
+
+
+class P2PExchange:
+    """WTA fused with its all-gather: each rank's WTA kernel stores its packed minima straight into
+    every rank's gather buffer over NVLink peer memory (psm_disp_select_keys_p2p).  Buffers are
+    shared between the per-GPU processes through CUDA IPC handles exchanged once at set-up.
+
+    Per frame: select() on every rank, one tiny barrier collective on the same stream, reduce()."""
+
+    def __init__(self, de, world, rank, group=None):
+        import torch
+        import torch.distributed as dist
+        self.de, self.world, self.rank, self.group = de, world, rank, group
+        L = capi.lib()
+        own = C.c_void_p()
+        capi.check(L.psm_p2p_create_buffer(de.handle, world, C.byref(own)), de.handle)
+        handle = C.create_string_buffer(64)
+        capi.check(L.psm_ipc_export(de.handle, own, handle), de.handle)
+        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).cuda()
+        allh = torch.empty((world, 64), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allh.view(-1), mine, group=group)
+        allh = allh.cpu().numpy()
+        ptrs = (C.c_void_p * world)()
+        for r in range(world):
+            if r == rank:
+                ptrs[r] = own.value
+            else:
+                p = C.c_void_p()
+                capi.check(L.psm_ipc_import(de.handle, allh[r].tobytes(), C.byref(p)), de.handle)
+                ptrs[r] = p.value
+        capi.check(L.psm_p2p_set_peers(de.handle, ptrs, world, rank), de.handle)
+        self._flag = torch.zeros(1, device="cuda")
+        dist.barrier(group=group)
+
+    def select(self):
+        capi.check(capi.lib().psm_disp_select_keys_p2p(self.de.handle), self.de.handle)
+
+    def barrier(self):
+        import torch.distributed as dist
+        dist.all_reduce(self._flag, group=self.group)  # stream-ordered cross-rank barrier
+
+    def reduce(self, lmap_ptr=None, rmap_ptr=None):
+        capi.check(capi.lib().psm_disp_reduce_p2p(self.de.handle, lmap_ptr, self.de.wid, rmap_ptr, self.de.wid),
+                   self.de.handle)

@@ -281,3 +281,36 @@ def test_cpp_dispest_facade_demo(tmp_path, scenes, oracle_scene_results):
     rd = np.fromfile(tmp_path / "r.u8", np.uint8).reshape(H, W)
     assert_same(ld, oracle_scene_results["Teddy"]["ld"], "C++ facade lDisMap")
     assert_same(rd, oracle_scene_results["Teddy"]["rd"], "C++ facade rDisMap")
+
+
+def test_fused_wta_p2p_gather_matches_unsharded(scenes, oracle_scene_results):
+    """psm_disp_select_keys_p2p: the WTA kernel of each shard stores its packed minima into every
+    shard's gather buffer (here both buffers live on the one GPU; across processes they are peer
+    mappings).  Two frames exercise the parity double-buffering."""
+    _, _, l, r = scenes["Teddy"]
+    H, W, _ = l.shape
+    L = capi.lib()
+    shards = [DispEst(l, r, 64, d_begin=0, d_count=40), DispEst(l, r, 64, d_begin=40, d_count=24)]
+    try:
+        bufs = (C.c_void_p * 2)()
+        for k, de in enumerate(shards):
+            p = C.c_void_p()
+            capi.check(L.psm_p2p_create_buffer(de.handle, 2, C.byref(p)), de.handle)
+            bufs[k] = p.value
+        for k, de in enumerate(shards):
+            capi.check(L.psm_p2p_set_peers(de.handle, bufs, 2, k), de.handle)
+        for frame in range(2):
+            for de in shards:
+                de.CostConst_GPU(); de.CostFilter_GPU()
+                capi.check(L.psm_disp_select_keys_p2p(de.handle), de.handle)
+            for de in shards:
+                de.sync()
+            for de in shards:
+                ld = np.zeros((H, W), np.uint8); rd = np.zeros((H, W), np.uint8)
+                capi.check(L.psm_disp_reduce_p2p(de.handle, ld.ctypes.data_as(C.c_void_p), W,
+                                                 rd.ctypes.data_as(C.c_void_p), W), de.handle)
+                assert_same(ld, oracle_scene_results["Teddy"]["ld"], f"p2p lDisMap frame {frame}")
+                assert_same(rd, oracle_scene_results["Teddy"]["rd"], f"p2p rDisMap frame {frame}")
+    finally:
+        for de in shards:
+            de.close()
