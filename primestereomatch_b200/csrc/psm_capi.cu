@@ -187,18 +187,18 @@ int launch_cvf_stream(psm_ctx* c)
     plan_segments(c->H, target_rows, &P.nseg, &P.seg_rows);
     const size_t smem = (size_t)8 * 4 * kCvfThreads * sizeof(float4);
     if (!c->cvf_attr_set) {
-        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->cvf_attr_set = true;
     }
     const unsigned grid = 2u * P.nseg * P.nstrips * P.ndgroups;
     switch (c->cvf_variant) {  // tuning variants (PSM option 100); 0 is the shipped default
-    case 1: cvf_stream_kernel<2, false><<<grid, kCvfThreads, smem, c->stream>>>(P); break;
-    case 2: cvf_stream_kernel<3, true><<<grid, kCvfThreads, smem, c->stream>>>(P); break;
-    case 3: cvf_stream_kernel<2, true><<<grid, kCvfThreads, smem, c->stream>>>(P); break;
-    default: cvf_stream_kernel<3, false><<<grid, kCvfThreads, smem, c->stream>>>(P); break;
+    case 1: cvf_stream_kernel<2, 0><<<grid, kCvfThreads, smem, c->stream>>>(P); break;
+    case 2: cvf_stream_kernel<3, 1><<<grid, kCvfThreads, smem, c->stream>>>(P); break;
+    case 3: cvf_stream_kernel<3, 2><<<grid, kCvfThreads, smem, c->stream>>>(P); break;
+    default: cvf_stream_kernel<3, 0><<<grid, kCvfThreads, smem, c->stream>>>(P); break;
     }
     PSM_LAUNCH_CHECK(c);
     return PSM_OK;

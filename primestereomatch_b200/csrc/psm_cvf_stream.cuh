@@ -88,6 +88,18 @@ __device__ __forceinline__ void hsum8(const double c[4], double h[4])
     h[3] = (S1 + Tn) + Q3;
 }
 
+// f32 -> f64 without the conversion pipe: for a positive normal float the double is
+// {hi = (u >> 3) + 0x38000000, lo = u << 29}; everything else (zero, denormal, negative, inf, nan)
+// takes the F2F instruction under a predicate that is almost never set.  Stage-1 inputs (p and
+// I*p) are non-negative, so on real data the XU pipe is spared these conversions.
+__device__ __forceinline__ double widen_pos(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    double d = __hiloint2double((int)((u >> 3) + 0x38000000u), (int)(u << 29));
+    if (u - 0x00800000u >= 0x7f000000u) d = (double)f;
+    return d;
+}
+
 __device__ __forceinline__ float mean64(double s) { return (float)__dmul_rn(s, 1.0 / 64.0); }
 
 __device__ __forceinline__ float4 ldg4(const char* __restrict__ p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -95,12 +107,13 @@ __device__ __forceinline__ float4 ldg4(const char* __restrict__ p) { return __ld
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // MINB: resident CTAs per SM the register allocation is sized for (3 -> <=168 regs, 2 -> <=255);
-// SKEW: run stage 2 of row t-1 next to stage 1 of row t in the steady loop (two independent streams).
-template <int MINB, bool SKEW>
+// IW: integer widening (widen_pos) of the stage-1 inputs: 0 none, 1 oldest rows, 2 newest + oldest rows.
+template <int MINB, int IW>
 __global__ void __launch_bounds__(kCvfThreads, MINB)
 cvf_stream_kernel(const CvfParams P)
 {
     extern __shared__ float4 ring[];  // [8 slots][4 planes][128 threads]
+    constexpr bool IWN = IW >= 2, IWO = IW >= 1;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int nthr = kCvfThreads;
@@ -175,10 +188,10 @@ cvf_stream_kernel(const CvfParams P)
         const f2x2 m0 = mul2(from4(x.i0), p), m1 = mul2(from4(x.i1), p), m2 = mul2(from4(x.i2), p);  // CVF.cpp:87
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            S1[0][j] = __dadd_rn(S1[0][j], (double)get(p, j));
-            S1[1][j] = __dadd_rn(S1[1][j], (double)get(m0, j));
-            S1[2][j] = __dadd_rn(S1[2][j], (double)get(m1, j));
-            S1[3][j] = __dadd_rn(S1[3][j], (double)get(m2, j));
+            S1[0][j] = __dadd_rn(S1[0][j], IWN ? widen_pos(get(p, j)) : (double)get(p, j));
+            S1[1][j] = __dadd_rn(S1[1][j], IWN ? widen_pos(get(m0, j)) : (double)get(m0, j));
+            S1[2][j] = __dadd_rn(S1[2][j], IWN ? widen_pos(get(m1, j)) : (double)get(m1, j));
+            S1[3][j] = __dadd_rn(S1[3][j], IWN ? widen_pos(get(m2, j)) : (double)get(m2, j));
         }
     };
     auto sub_row = [&](const RowIn& x) {
@@ -186,10 +199,10 @@ cvf_stream_kernel(const CvfParams P)
         const f2x2 m0 = mul2(from4(x.i0), p), m1 = mul2(from4(x.i1), p), m2 = mul2(from4(x.i2), p);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            S1[0][j] = __dsub_rn(S1[0][j], (double)get(p, j));
-            S1[1][j] = __dsub_rn(S1[1][j], (double)get(m0, j));
-            S1[2][j] = __dsub_rn(S1[2][j], (double)get(m1, j));
-            S1[3][j] = __dsub_rn(S1[3][j], (double)get(m2, j));
+            S1[0][j] = __dsub_rn(S1[0][j], IWO ? widen_pos(get(p, j)) : (double)get(p, j));
+            S1[1][j] = __dsub_rn(S1[1][j], IWO ? widen_pos(get(m0, j)) : (double)get(m0, j));
+            S1[2][j] = __dsub_rn(S1[2][j], IWO ? widen_pos(get(m1, j)) : (double)get(m1, j));
+            S1[3][j] = __dsub_rn(S1[3][j], IWO ? widen_pos(get(m2, j)) : (double)get(m2, j));
         }
     };
     auto load_guide = [&](size_t ro, float4 (&g4)[10]) {
@@ -348,29 +361,11 @@ cvf_stream_kernel(const CvfParams P)
             emit(ro_y, o0, o1, o2);
             ro_y += rowB;
         };
-        if (!SKEW) {
-            for (; t <= Ts1; ++t) {
-                const float4 o0 = ldg4(Go + ro_y), o1 = ldg4(Go + (planeB + ro_y)), o2 = ldg4(Go + (2 * planeB + ro_y));
-                f2x2 av[4];
-                stage1(av);
-                stage2(t, av, o0, o1, o2);
-            }
-        } else {
-            // software-skewed: stage 2 of row t-1 and stage 1 of row t are independent instruction
-            // streams inside one loop body, so each hides the other's pipe latencies
-            f2x2 avp[4];
-            stage1(avp);
-            int tp = t++;
-            for (; t <= Ts1; ++t) {
-                const float4 o0 = ldg4(Go + ro_y), o1 = ldg4(Go + (planeB + ro_y)), o2 = ldg4(Go + (2 * planeB + ro_y));
-                f2x2 avc[4];
-                stage1(avc);
-                stage2(tp, avp, o0, o1, o2);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) avp[q] = avc[q];
-                tp = t;
-            }
-            stage2(tp, avp, ldg4(Go + ro_y), ldg4(Go + (planeB + ro_y)), ldg4(Go + (2 * planeB + ro_y)));
+        for (; t <= Ts1; ++t) {
+            const float4 o0 = ldg4(Go + ro_y), o1 = ldg4(Go + (planeB + ro_y)), o2 = ldg4(Go + (2 * planeB + ro_y));
+            f2x2 av[4];
+            stage1(av);
+            stage2(t, av, o0, o1, o2);
         }
     }
     for (; t <= Tend; ++t) generic_step(t);

@@ -314,3 +314,53 @@ def test_fused_wta_p2p_gather_matches_unsharded(scenes, oracle_scene_results):
     finally:
         for de in shards:
             de.close()
+
+
+def test_max_disparity_256(oracle):
+    """D = 256 (BASELINE config C5 depth): disparities up to 255 must survive the u8 maps
+    (the reference's OpenCL WTA keeps the index in a signed char, dispsel.cl:96; ours is unsigned)."""
+    W, H, D = 400, 48, 256
+    l8, r8, _ = synth.stereo_pair_u8(W, H, D, seed=9)
+    rng = np.random.default_rng(2)
+    r8 = np.clip(r8.astype(np.int16) + rng.integers(-3, 4, r8.shape), 0, 255).astype(np.uint8)
+    l, r = synth.to_f32(l8), synth.to_f32(r8)
+    ref = oracle.pipeline(l, r, D, keep_volumes=True)
+    g = run_gpu(l, r, D)
+    assert_same(g["lf"], ref["lVol"], "left filtered D=256")
+    assert_same(g["ld"], ref["lDis"], "lDisMap D=256")
+    assert_same(g["rd"], ref["rDis"], "rDisMap D=256")
+    assert int(ref["lDis"].max()) > 127  # the test really exercises indices a signed char cannot hold
+
+
+def test_c5_shape_sharded_eight_ways_on_one_gpu(oracle):
+    """BASELINE config C5 structure (D=256 split over 8 ranks, 32 slices each) at a reduced image
+    size: eight shard contexts on one GPU, fused WTA+gather buffers, result == unsharded oracle."""
+    W, H, D, G = 256, 40, 256, 8
+    l8, r8, _ = synth.stereo_pair_u8(W, H, D, seed=21)
+    rng = np.random.default_rng(5)
+    r8 = np.clip(r8.astype(np.int16) + rng.integers(-3, 4, r8.shape), 0, 255).astype(np.uint8)
+    l, r = synth.to_f32(l8), synth.to_f32(r8)
+    ref = oracle.pipeline(l, r, D)
+    L = capi.lib()
+    from primestereomatch_b200.sharding import shard_range
+    shards = [DispEst(l, r, D, d_begin=shard_range(D, G, k)[0], d_count=shard_range(D, G, k)[1]) for k in range(G)]
+    try:
+        bufs = (C.c_void_p * G)()
+        for k, de in enumerate(shards):
+            p = C.c_void_p()
+            capi.check(L.psm_p2p_create_buffer(de.handle, G, C.byref(p)), de.handle)
+            bufs[k] = p.value
+        for k, de in enumerate(shards):
+            capi.check(L.psm_p2p_set_peers(de.handle, bufs, G, k), de.handle)
+            de.CostConst_GPU(); de.CostFilter_GPU()
+            capi.check(L.psm_disp_select_keys_p2p(de.handle), de.handle)
+        for de in shards:
+            de.sync()
+        ld = np.zeros((H, W), np.uint8); rd = np.zeros((H, W), np.uint8)
+        capi.check(L.psm_disp_reduce_p2p(shards[3].handle, ld.ctypes.data_as(C.c_void_p), W,
+                                         rd.ctypes.data_as(C.c_void_p), W), shards[3].handle)
+        assert_same(ld, ref["lDis"], "8-way sharded lDisMap")
+        assert_same(rd, ref["rDis"], "8-way sharded rDisMap")
+    finally:
+        for de in shards:
+            de.close()

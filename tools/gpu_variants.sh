@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in 0 1 2 3; do
+for v in 0 2 3; do
   python bench.py --steps 10 --warmup 3 --no-cpu-baseline --variant $v 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
