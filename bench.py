@@ -221,7 +221,9 @@ def main():
             capi.check(L.psm_disp_reduce_keys(de.handle, gathered[0].data_ptr(), gathered[1].data_ptr(), world,
                                               out_l, W, out_r, W), de.handle)
 
-    def timed(e2e, steps, collect_kernel=False):
+    def timed(e2e, steps):
+        """K steps bracketed by barrier + synchronize on both sides, CUDA events on the launching
+        stream, max over ranks.  No host synchronisation inside the region."""
         for _ in range(warm):
             step(e2e)
         torch.cuda.synchronize()
@@ -229,12 +231,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kms = []
         e0.record(stream)
         for _ in range(steps):
             step(e2e)
-            if collect_kernel:
-                kms.append(de.stage_ms(4))  # the fused CVF kernel alone, cudaEvents on the launching stream
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -242,17 +241,28 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), kms
+        return float(ms.item())
+
+    def kernel_times(steps):
+        """Duration of the fused CVF kernel alone (cudaEvent pair around that launch, on the launching
+        stream) for `steps` further steps of the same workload; reading an event pair needs a host
+        sync per step, which is why this is a separate loop from the throughput measurement."""
+        out = []
+        for _ in range(steps):
+            step(False)
+            out.append(de.stage_ms(4))
+        return out
 
     launches0 = de.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    total_ms, kms = timed(False, args.steps, collect_kernel=True)
-    clocks = sampler.stop() if rank == 0 else None
+    total_ms = timed(False, args.steps)
     launches_per_step = (de.launch_count() - launches0) // (warm + args.steps)
+    kms = kernel_times(args.steps)
+    clocks = sampler.stop() if rank == 0 else None
     stage = {n: de.stage_ms(i) for i, n in enumerate(["ingest", "cvc", "cvf", "wta", "cvf_kernel"])}
-    e2e_ms, _ = timed(True, args.steps)
+    e2e_ms = timed(True, args.steps)
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
