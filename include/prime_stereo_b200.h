@@ -61,7 +61,7 @@ enum {
 };
 enum {
     PSM_CVF_EXACT = 0, /* streaming fused kernel, every box sum accumulated in fp64: bit-exact q */
-    PSM_CVF_MIXED = 1, /* stage-1 boxes fp64 (a,b bit-exact), stage-2 boxes fp32: |dq| ~1e-6 */
+    PSM_CVF_MIXED = 1, /* reserved (fp32 second stage); not built: psm_set_option returns PSM_EINVAL */
     PSM_CVF_NAIVE = 2  /* unfused two-pass direct 64-tap fp64 kernels: slow device-side cross-check */
 };
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 # scaling run the way the driver does it: N = 1,2,4,8 back to back
 mkdir -p gpurun_out
-for n in 1 2 4 8; do
+for n in ${NLIST:-1 2 4 8}; do
   if [ $n -eq 1 ]; then
     timeout 600 python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/scale_n1.log 2>&1
   else
