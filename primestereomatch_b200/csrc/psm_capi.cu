@@ -136,11 +136,14 @@ int ingest(psm_ctx* c, const T* l, size_t lstep, const T* r, size_t rstep, bool 
 int ensure_guide(psm_ctx* c)
 {
     if (c->guide_valid) return PSM_OK;
-    for (int v = 0; v < 2; ++v) {
-        dim3 blk(128), grd((c->W + 3 + 127) / 128, (c->H + kGuideSegRows - 1) / kGuideSegRows);
-        guide_kernel<<<grd, blk, 0, c->stream>>>(c->guide[v], c->plane, c->W, c->H, c->Wp);
-        PSM_LAUNCH_CHECK(c);
-    }
+    GuideParams P;
+    P.guide[0] = c->guide[0]; P.guide[1] = c->guide[1];
+    P.W = c->W; P.H = c->H; P.Wp = c->Wp;
+    P.nstrips = (c->W + kGuideStripOut - 1) / kGuideStripOut;
+    P.nseg = (c->H + kGuideSegRows - 1) / kGuideSegRows;
+    const int tasks = 2 * P.nstrips * P.nseg;  // one warp each
+    guide_kernel<<<(tasks + 3) / 4, 128, 0, c->stream>>>(P);
+    PSM_LAUNCH_CHECK(c);
     c->guide_valid = true;
     return PSM_OK;
 }

@@ -72,22 +72,6 @@ template <int J> __device__ __forceinline__ float get(const f2x2& v)
 }
 __device__ __forceinline__ float get(const f2x2& v, int j) { return j == 0 ? v.lo.x : (j == 1 ? v.lo.y : (j == 2 ? v.hi.x : v.hi.y)); }
 
-// 8-wide window sums from the 4 owned column sums c[0..3]:
-// h[j] = columns (4l+j) .. (4l+j+7) = suffix_l[j..3] + total_{l+1} + prefix_{l+2}[0..j-1]
-__device__ __forceinline__ void hsum8(const double c[4], double h[4])
-{
-    const double P1 = c[0], P2 = c[0] + c[1], P3 = P2 + c[2], Tt = P3 + c[3];
-    const double S1 = c[3], S2 = c[2] + c[3], S3 = c[1] + S2;
-    const double Tn = __shfl_down_sync(0xffffffffu, Tt, 1);
-    const double Q1 = __shfl_down_sync(0xffffffffu, P1, 2);
-    const double Q2 = __shfl_down_sync(0xffffffffu, P2, 2);
-    const double Q3 = __shfl_down_sync(0xffffffffu, P3, 2);
-    h[0] = Tt + Tn;
-    h[1] = (S3 + Tn) + Q1;
-    h[2] = (S2 + Tn) + Q2;
-    h[3] = (S1 + Tn) + Q3;
-}
-
 // f32 -> f64 without the conversion pipe: for a positive normal float the double is
 // {hi = (u >> 3) + 0x38000000, lo = u << 29}; everything else (zero, denormal, negative, inf, nan)
 // takes the F2F instruction under a predicate that is almost never set.  Stage-1 inputs (p and

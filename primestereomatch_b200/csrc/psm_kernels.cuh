@@ -225,97 +225,133 @@ __device__ __forceinline__ float box8_direct(F tap, int x, int y, int W, int H)
 // ------------------------------------------------------------------------------------------
 constexpr int kGuideI = 0, kGuideMean = 3, kGuideAdj = 6, kGuideIdet = 12, kGuideVar = 13, kGuidePlanes = 19;
 
-// One thread = one column of one row segment.  Horizontal taps x-4 .. x+3 come straight from the
-// mirrored column halo of the I planes (pad_cols_kernel has run); rows reflect by index.
-__device__ __forceinline__ void guide_row_sums(const float* __restrict__ I0, size_t plane, size_t ro, int x, double s[9])
+// d-independent per-pixel terms from the nine box means m[0..8] = mean of I0,I1,I2, I0I0,I0I1,I0I2,I1I1,I1I2,I2I2:
+// var_I (CVF.cpp:60-69), symmetric adjugate of (Sigma + eps I) and 1/det (CVF.cpp:108-120).
+__device__ __forceinline__ void guide_solve(const float m[9], float v[6], float M[6], float& idet)
 {
-    const float* p0 = I0 + ro + x;
-    const float* p1 = p0 + plane;
-    const float* p2 = p1 + plane;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) s[k] = 0.0;
-#pragma unroll
-    for (int dx = -kBoxAnchor; dx < kBoxK - kBoxAnchor; ++dx) {
-        const float a = __ldg(p0 + dx), b = __ldg(p1 + dx), c = __ldg(p2 + dx);
-        s[0] = __dadd_rn(s[0], (double)a);
-        s[1] = __dadd_rn(s[1], (double)b);
-        s[2] = __dadd_rn(s[2], (double)c);
-        s[3] = __dadd_rn(s[3], (double)fmul(a, a));  // rr   (CVF.cpp:62 multiply)
-        s[4] = __dadd_rn(s[4], (double)fmul(a, b));  // rg
-        s[5] = __dadd_rn(s[5], (double)fmul(a, c));  // rb
-        s[6] = __dadd_rn(s[6], (double)fmul(b, b));  // gg
-        s[7] = __dadd_rn(s[7], (double)fmul(b, c));  // gb
-        s[8] = __dadd_rn(s[8], (double)fmul(c, c));  // bb
-    }
+    v[0] = fsub(m[3], fmul(m[0], m[0]));
+    v[1] = fsub(m[4], fmul(m[0], m[1]));
+    v[2] = fsub(m[5], fmul(m[0], m[2]));
+    v[3] = fsub(m[6], fmul(m[1], m[1]));
+    v[4] = fsub(m[7], fmul(m[1], m[2]));
+    v[5] = fsub(m[8], fmul(m[2], m[2]));
+    const float a11 = fadd(v[0], kGifEps), a12 = v[1], a13 = v[2];
+    const float a21 = v[1], a22 = fadd(v[3], kGifEps), a23 = v[4];
+    const float a31 = v[2], a32 = v[4], a33 = fadd(v[5], kGifEps);
+    // cofactors exactly as written at CVF.cpp:117-146 (the adjugate is symmetric bit-for-bit
+    // because each mirrored entry is the same two products in commuted order)
+    M[0] = fsub(fmul(a33, a22), fmul(a32, a23));  // M00
+    M[1] = fsub(fmul(a31, a23), fmul(a33, a21));  // M01
+    M[2] = fsub(fmul(a32, a21), fmul(a31, a22));  // M02
+    M[3] = fsub(fmul(a33, a11), fmul(a31, a13));  // M11
+    M[4] = fsub(fmul(a31, a12), fmul(a32, a11));  // M12
+    M[5] = fsub(fmul(a22, a11), fmul(a21, a12));  // M22
+    // DET = a11*(a33*a22-a32*a23) - a21*(a33*a12-a32*a13) + a31*(a23*a12-a22*a13)  (CVF.cpp:117-119)
+    const float t1 = fsub(fmul(a33, a12), fmul(a32, a13));
+    const float t2 = fsub(fmul(a23, a12), fmul(a22, a13));
+    const float det = fadd(fsub(fmul(a11, M[0]), fmul(a21, t1)), fmul(a31, t2));
+    idet = __fdiv_rn(1.0f, det);  // CVF.cpp:120
 }
 
-constexpr int kGuideSegRows = 32;
-
-__global__ void __launch_bounds__(128) guide_kernel(float* __restrict__ guide, size_t plane, int W, int H, int Wp)
+// 8-wide window sums from the 4 column sums c[0..3] a lane owns:
+// h[j] = columns (4l+j) .. (4l+j+7) = suffix_l[j..3] + total_{l+1} + prefix_{l+2}[0..j-1]   (4 fp64 shuffles)
+__device__ __forceinline__ void hsum8(const double c[4], double h[4])
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= ((W + 3) & ~3)) return;
-    const int y0 = blockIdx.y * kGuideSegRows;
+    const double P1 = c[0], P2 = c[0] + c[1], P3 = P2 + c[2], Tt = P3 + c[3];
+    const double S1 = c[3], S2 = c[2] + c[3], S3 = c[1] + S2;
+    const double Tn = __shfl_down_sync(0xffffffffu, Tt, 1);
+    const double Q1 = __shfl_down_sync(0xffffffffu, P1, 2);
+    const double Q2 = __shfl_down_sync(0xffffffffu, P2, 2);
+    const double Q3 = __shfl_down_sync(0xffffffffu, P3, 2);
+    h[0] = Tt + Tn;
+    h[1] = (S3 + Tn) + Q1;
+    h[2] = (S2 + Tn) + Q2;
+    h[3] = (S1 + Tn) + Q3;
+}
+
+// K2: warp = strip of 128 input columns (120 output columns) x kGuideSegRows rows of one view;
+// lane = 4 columns.  fp64 running column sums of the nine planes (newest row added, oldest row
+// removed, both re-read from the I planes whose column halo is mirrored), 8-wide row sums by
+// hsum8, then guide_solve per pixel; every plane is written with 128-bit stores.
+constexpr int kGuideSegRows = 32;
+constexpr int kGuideStripOut = 120;
+
+struct GuideParams {
+    float* guide[2];
+    int W, H, Wp, nstrips, nseg;
+};
+
+__global__ void __launch_bounds__(128) guide_kernel(const GuideParams P)
+{
+    const int lane = threadIdx.x & 31;
+    int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int strip = task % P.nstrips; task /= P.nstrips;
+    const int seg = task % P.nseg;
+    const int view = task / P.nseg;
+    if (view >= 2) return;
+    const int W = P.W, H = P.H, Wp = P.Wp;
+    const size_t plane = (size_t)H * Wp;
+    float* __restrict__ G = P.guide[view];
+    const int cin = strip * kGuideStripOut - 4 + 4 * lane;  // input columns; outputs are cin+4 .. cin+7
+    const int co = cin + 4;
+    const bool in_ok = cin <= W + 4;       // beyond: nothing this lane feeds is ever stored (and the halo ends at W+7)
+    const bool out_ok = lane <= 29 && co < W;
+    const int y0 = seg * kGuideSegRows;
     const int y1 = min(H, y0 + kGuideSegRows);
-    if (x >= W) {
-        for (int y = y0; y < y1; ++y)
-            for (int k = kGuideMean; k < kGuidePlanes; ++k) guide[k * plane + (size_t)y * Wp + x] = 0.f;
-        return;
-    }
-    double V[9], s[9];
+
+    double V[9][4];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) V[k] = 0.0;
-    for (int r = y0 - kBoxAnchor; r < y0 + kBoxK - kBoxAnchor - 1; ++r) {
-        guide_row_sums(guide, plane, (size_t)reflect101(r, H) * Wp, x, s);
+    for (int k = 0; k < 9; ++k)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) V[k] = __dadd_rn(V[k], s[k]);
-    }
+        for (int j = 0; j < 4; ++j) V[k][j] = 0.0;
+
+    auto feed = [&](int r, const bool add) {
+        const size_t ro = (size_t)reflect101(r, H) * Wp + cin;
+        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4, c4 = a4;
+        if (in_ok) {
+            a4 = __ldg(reinterpret_cast<const float4*>(G + ro));
+            b4 = __ldg(reinterpret_cast<const float4*>(G + plane + ro));
+            c4 = __ldg(reinterpret_cast<const float4*>(G + 2 * plane + ro));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = comp(a4, j), b = comp(b4, j), c = comp(c4, j);
+            const float t[9] = {a, b, c, fmul(a, a), fmul(a, b), fmul(a, c), fmul(b, b), fmul(b, c), fmul(c, c)};  // CVF.cpp:62
+#pragma unroll
+            for (int k = 0; k < 9; ++k) V[k][j] = add ? __dadd_rn(V[k][j], (double)t[k]) : __dsub_rn(V[k][j], (double)t[k]);
+        }
+    };
+
+    for (int r = y0 - kBoxAnchor; r < y0 + kBoxK - kBoxAnchor - 1; ++r) feed(r, true);
     for (int y = y0; y < y1; ++y) {
-        guide_row_sums(guide, plane, (size_t)reflect101(y + kBoxK - kBoxAnchor - 1, H) * Wp, x, s);
-        float m[9];
+        feed(y + kBoxK - kBoxAnchor - 1, true);
+        float m[9][4];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) { V[k] = __dadd_rn(V[k], s[k]); m[k] = (float)__dmul_rn(V[k], 1.0 / 64.0); }
-        guide_row_sums(guide, plane, (size_t)reflect101(y - kBoxAnchor, H) * Wp, x, s);
+        for (int k = 0; k < 9; ++k) {
+            double h[4];
+            hsum8(V[k], h);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) V[k] = __dsub_rn(V[k], s[k]);
-        const size_t o = (size_t)y * Wp + x;
-        // var_I[idx] = box(I_c * I_c') - mean_c * mean_c'   (CVF.cpp:60-69)
-        float v[6];
-        v[0] = fsub(m[3], fmul(m[0], m[0]));
-        v[1] = fsub(m[4], fmul(m[0], m[1]));
-        v[2] = fsub(m[5], fmul(m[0], m[2]));
-        v[3] = fsub(m[6], fmul(m[1], m[1]));
-        v[4] = fsub(m[7], fmul(m[1], m[2]));
-        v[5] = fsub(m[8], fmul(m[2], m[2]));
-        // CVF.cpp:108-116
-        const float a11 = fadd(v[0], kGifEps), a12 = v[1], a13 = v[2];
-        const float a21 = v[1], a22 = fadd(v[3], kGifEps), a23 = v[4];
-        const float a31 = v[2], a32 = v[4], a33 = fadd(v[5], kGifEps);
-        // cofactors exactly as written at CVF.cpp:117-146 (the adjugate is symmetric bit-for-bit
-        // because each mirrored entry is the same two products in commuted order)
-        const float M00 = fsub(fmul(a33, a22), fmul(a32, a23));
-        const float M01 = fsub(fmul(a31, a23), fmul(a33, a21));
-        const float M02 = fsub(fmul(a32, a21), fmul(a31, a22));
-        const float M11 = fsub(fmul(a33, a11), fmul(a31, a13));
-        const float M12 = fsub(fmul(a31, a12), fmul(a32, a11));
-        const float M22 = fsub(fmul(a22, a11), fmul(a21, a12));
-        // DET = a11*(a33*a22-a32*a23) - a21*(a33*a12-a32*a13) + a31*(a23*a12-a22*a13)  (CVF.cpp:117-119)
-        const float t1 = fsub(fmul(a33, a12), fmul(a32, a13));
-        const float t2 = fsub(fmul(a23, a12), fmul(a22, a13));
-        float det = fadd(fsub(fmul(a11, M00), fmul(a21, t1)), fmul(a31, t2));
-        det = __fdiv_rn(1.0f, det);  // CVF.cpp:120
-        guide[(kGuideMean + 0) * plane + o] = m[0];
-        guide[(kGuideMean + 1) * plane + o] = m[1];
-        guide[(kGuideMean + 2) * plane + o] = m[2];
-        guide[(kGuideAdj + 0) * plane + o] = M00;
-        guide[(kGuideAdj + 1) * plane + o] = M01;
-        guide[(kGuideAdj + 2) * plane + o] = M02;
-        guide[(kGuideAdj + 3) * plane + o] = M11;
-        guide[(kGuideAdj + 4) * plane + o] = M12;
-        guide[(kGuideAdj + 5) * plane + o] = M22;
-        guide[kGuideIdet * plane + o] = det;
-    #pragma unroll
-        for (int k = 0; k < 6; ++k) guide[(kGuideVar + k) * plane + o] = v[k];
+            for (int j = 0; j < 4; ++j) m[k][j] = (float)__dmul_rn(h[j], 1.0 / 64.0);
+        }
+        feed(y - kBoxAnchor, false);
+        float o[16][4];  // planes kGuideMean .. kGuidePlanes-1
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float mm[9] = {m[0][j], m[1][j], m[2][j], m[3][j], m[4][j], m[5][j], m[6][j], m[7][j], m[8][j]};
+            float v[6], M[6], idet;
+            guide_solve(mm, v, M, idet);
+            const bool px_ok = co + j < W;  // columns W .. W4-1 of the last group hold zeros
+            o[0][j] = px_ok ? mm[0] : 0.f; o[1][j] = px_ok ? mm[1] : 0.f; o[2][j] = px_ok ? mm[2] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { o[3 + k][j] = px_ok ? M[k] : 0.f; o[10 + k][j] = px_ok ? v[k] : 0.f; }
+            o[9][j] = px_ok ? idet : 0.f;
+        }
+        if (out_ok) {
+            const size_t oo = (size_t)y * Wp + co;
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                *reinterpret_cast<float4*>(G + (size_t)(kGuideMean + k) * plane + oo) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+        }
     }
 }
 
