@@ -209,9 +209,8 @@ def main():
             else:
                 capi.check(L.psm_disp_select_device(de.handle), de.handle)
         elif p2p is not None:
-            p2p.select()    # WTA + all-gather in one kernel (peer stores)
-            p2p.barrier()
-            p2p.reduce(lmap.data_ptr() if e2e else None, rmap.data_ptr() if e2e else None)
+            # WTA+scatter kernel, barrier, chunk-reduce+gather kernel, barrier (all over NVLink peer memory)
+            p2p.frame(lmap.data_ptr() if e2e else None, rmap.data_ptr() if e2e else None)
         else:
             capi.check(L.psm_disp_select_keys(de.handle, keys[0].data_ptr(), keys[1].data_ptr()), de.handle)
             dist.all_gather_into_tensor(gathered[0].view(-1), keys[0])

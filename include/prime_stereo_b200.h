@@ -128,21 +128,24 @@ int psm_disp_reduce_keys(psm_ctx* ctx, const uint64_t* d_gathered_left,
                          uint8_t* left, size_t left_step, uint8_t* right, size_t right_step);
 
 /* ---- Sharded stage 3 fused with its exchange over NVLink peer memory ------------------------------
- * Instead of "local WTA kernel, then a library all-gather", ONE kernel computes this rank's packed
- * minima and stores them straight into the gather buffer of every rank (P2P stores), so the
- * exchange rides on the kernel's own writes.  Every rank owns a gather buffer of
- * 2 (frame parity) x 2 (views) x nranks x H*W uint64, created with psm_p2p_create_buffer and shared
- * with the other processes through CUDA IPC (psm_ipc_export / psm_ipc_import).
- * Per frame: psm_disp_select_keys_p2p on every rank, one cross-rank barrier (e.g. a 1-element NCCL
- * all-reduce on the same stream), psm_disp_reduce_p2p on every rank.  Double buffering by frame
- * parity makes that single barrier sufficient. */
+ * Instead of "local WTA kernel, then library collectives", the min-reduction over ranks is done by two
+ * kernels that read/write PEER device memory directly (reduce-scatter + all-gather, hand-rolled):
+ *   psm_disp_select_keys_p2p : WTA over this rank's slices; the packed minimum of every pixel is stored
+ *                              straight into the exchange block of the rank that reduces that pixel;
+ *   psm_disp_reduce_p2p      : this rank reduces its pixel chunk over all ranks' minima and stores the
+ *                              winning disparity into EVERY rank's result map;
+ *   psm_disp_fetch_p2p       : copy this rank's (complete) result maps to host memory and synchronise.
+ * A cross-rank barrier (e.g. a 1-element NCCL all-reduce on the same stream) must separate select from
+ * reduce and reduce from fetch.  Every rank owns one exchange block (psm_p2p_create_buffer), shared with
+ * the other per-GPU processes through CUDA IPC (psm_ipc_export / psm_ipc_import). */
 int psm_p2p_create_buffer(psm_ctx* ctx, int nranks, void** d_buffer);
 int psm_ipc_export(psm_ctx* ctx, void* d_ptr, unsigned char handle_out[64]);
 int psm_ipc_import(psm_ctx* ctx, const unsigned char handle[64], void** d_ptr);
-/* d_buffers[r] = gather buffer of rank r as seen from this process (own pointer for r == rank). */
+/* d_buffers[r] = exchange block of rank r as seen from this process (own pointer for r == rank). */
 int psm_p2p_set_peers(psm_ctx* ctx, void* const* d_buffers, int nranks, int rank);
 int psm_disp_select_keys_p2p(psm_ctx* ctx);
-int psm_disp_reduce_p2p(psm_ctx* ctx, uint8_t* left, size_t left_step, uint8_t* right, size_t right_step);
+int psm_disp_reduce_p2p(psm_ctx* ctx);
+int psm_disp_fetch_p2p(psm_ctx* ctx, uint8_t* left, size_t left_step, uint8_t* right, size_t right_step);
 
 /* Debug / parity reads (synchronising). `d` is a GLOBAL disparity index owned by this context. */
 int psm_read_cost_slice(psm_ctx* ctx, int view, int d, float* dst, size_t dst_step);

@@ -16,7 +16,7 @@ SYMBOLS = [
     "psm_set_stream", "psm_set_images", "psm_set_images_u8", "psm_set_images_device",
     "psm_cost_const", "psm_cost_filter", "psm_disp_select", "psm_disp_select_device",
     "psm_disp_select_keys", "psm_disp_reduce_keys", "psm_p2p_create_buffer", "psm_ipc_export", "psm_ipc_import",
-    "psm_p2p_set_peers", "psm_disp_select_keys_p2p", "psm_disp_reduce_p2p", "psm_read_cost_slice", "psm_write_cost_slice",
+    "psm_p2p_set_peers", "psm_disp_select_keys_p2p", "psm_disp_reduce_p2p", "psm_disp_fetch_p2p", "psm_read_cost_slice", "psm_write_cost_slice",
     "psm_read_guide_plane", "psm_read_ab_slice", "psm_device_ptr", "psm_stage_ms",
     "psm_launch_count", "psm_sync", "psm_last_error", "psm_build_info",
 ]
@@ -66,7 +66,8 @@ def lib():
     L.psm_ipc_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.psm_p2p_set_peers.argtypes = [vp, C.POINTER(vp), i, i]
     L.psm_disp_select_keys_p2p.argtypes = [vp]
-    L.psm_disp_reduce_p2p.argtypes = [vp, u8p, sz, u8p, sz]
+    L.psm_disp_reduce_p2p.argtypes = [vp]
+    L.psm_disp_fetch_p2p.argtypes = [vp, u8p, sz, u8p, sz]
     L.psm_read_cost_slice.argtypes = [vp, i, i, fp, sz]
     L.psm_write_cost_slice.argtypes = [vp, i, i, fp, sz]
     L.psm_read_guide_plane.argtypes = [vp, i, i, fp, sz]

@@ -34,10 +34,10 @@ struct psm_ctx {
     float* vol_alt[2] = {nullptr, nullptr}; // the other half of the ping-pong
     void* stage_in[2] = {nullptr, nullptr}; // device staging for the interleaved upload
     uint8_t* dis[2] = {nullptr, nullptr};
-    unsigned long long* p2p_own = nullptr;  // own gather buffer [2 parity][2 views][nranks][H*W]
-    unsigned long long* p2p_peer[8] = {};   // every rank's gather buffer as mapped here
+    unsigned char* p2p_own = nullptr;       // own exchange block: keys [2 views][nranks][chunk] u64 + maps [2 views][H*W] u8
+    unsigned char* p2p_peer[8] = {};        // every rank's exchange block as mapped here
     void* p2p_imported[8] = {};             // IPC mappings to close at destroy
-    int p2p_nimported = 0, p2p_nranks = 0, p2p_rank = 0, p2p_parity = 0;
+    int p2p_nimported = 0, p2p_nranks = 0, p2p_rank = 0;
     float* alloc[16] = {};                  // raw cudaMalloc pointers behind the halo-offset pointers above
     int nalloc = 0;
     bool cvf_attr_set = false;
@@ -497,14 +497,18 @@ int psm_disp_reduce_keys(psm_ctx* c, const uint64_t* d_gathered_left, const uint
     return PSM_OK;
 }
 
+// Exchange block of one rank: [2 views][nranks][chunk] uint64 keys, then [2 views][H*W] u8 result maps.
+static size_t p2p_chunk(const psm_ctx* c, int nranks) { return ((size_t)c->W * c->H + nranks - 1) / nranks; }
+static size_t p2p_keys_bytes(const psm_ctx* c, int nranks) { return (size_t)2 * nranks * p2p_chunk(c, nranks) * sizeof(unsigned long long); }
+
 int psm_p2p_create_buffer(psm_ctx* c, int nranks, void** d_buffer)
 {
     if (int rc = bind(c)) return rc;
     if (nranks < 1 || nranks > 8 || !d_buffer) return fail(c, PSM_EINVAL, "bad nranks %d (1..8)", nranks);
     if (c->p2p_own) { cudaFree(c->p2p_own); c->p2p_own = nullptr; }
-    const size_t n = (size_t)4 * nranks * c->W * c->H;
-    PSM_CUDA(c, cudaMalloc(&c->p2p_own, n * sizeof(unsigned long long)));
-    PSM_CUDA(c, cudaMemsetAsync(c->p2p_own, 0xff, n * sizeof(unsigned long long), c->stream));
+    const size_t bytes = p2p_keys_bytes(c, nranks) + (size_t)2 * c->W * c->H;
+    PSM_CUDA(c, cudaMalloc(&c->p2p_own, bytes));
+    PSM_CUDA(c, cudaMemsetAsync(c->p2p_own, 0xff, bytes, c->stream));
     PSM_CUDA(c, cudaStreamSynchronize(c->stream));
     c->p2p_nranks = nranks;
     *d_buffer = c->p2p_own;
@@ -538,11 +542,22 @@ int psm_p2p_set_peers(psm_ctx* c, void* const* d_buffers, int nranks, int rank)
     if (nranks != c->p2p_nranks || rank < 0 || rank >= nranks) return fail(c, PSM_EINVAL, "bad peers (nranks %d, rank %d)", nranks, rank);
     for (int r = 0; r < nranks; ++r) {
         if (!d_buffers[r]) return fail(c, PSM_EINVAL, "null buffer for rank %d", r);
-        c->p2p_peer[r] = static_cast<unsigned long long*>(d_buffers[r]);
+        c->p2p_peer[r] = static_cast<unsigned char*>(d_buffers[r]);
     }
     c->p2p_rank = rank;
-    c->p2p_parity = 0;
     return PSM_OK;
+}
+
+static void p2p_fill(const psm_ctx* c, int view, P2pPeers& peers)
+{
+    const size_t chunk = p2p_chunk(c, c->p2p_nranks);
+    const size_t npix = (size_t)c->W * c->H;
+    peers.nranks = c->p2p_nranks; peers.rank = c->p2p_rank; peers.chunk = (unsigned)chunk;
+    for (int r = 0; r < 8; ++r) {
+        unsigned char* base = r < c->p2p_nranks ? c->p2p_peer[r] : nullptr;
+        peers.keys[r] = base ? reinterpret_cast<unsigned long long*>(base) + (size_t)view * c->p2p_nranks * chunk : nullptr;
+        peers.maps[r] = base ? base + p2p_keys_bytes(c, c->p2p_nranks) + (size_t)view * npix : nullptr;
+    }
 }
 
 int psm_disp_select_keys_p2p(psm_ctx* c)
@@ -550,34 +565,37 @@ int psm_disp_select_keys_p2p(psm_ctx* c)
     if (int rc = bind(c)) return rc;
     if (!c->p2p_own || !c->p2p_peer[0]) return fail(c, PSM_ESTATE, "psm_p2p_create_buffer / psm_p2p_set_peers first");
     if (int rc = stage_begin(c, 3)) return rc;
-    const size_t npix = (size_t)c->W * c->H;
-    c->p2p_parity ^= 1;
     for (int v = 0; v < 2; ++v) {
         P2pPeers peers;
-        peers.nranks = c->p2p_nranks; peers.rank = c->p2p_rank;
-        for (int r = 0; r < 8; ++r)
-            peers.buf[r] = r < c->p2p_nranks ? c->p2p_peer[r] + ((size_t)c->p2p_parity * 2 + v) * c->p2p_nranks * npix : nullptr;
+        p2p_fill(c, v, peers);
         dim3 blk(256), grd(((c->W + 3) / 4 + 255) / 256, c->H);
-        wta_p2p_kernel<<<grd, blk, 0, c->stream>>>(c->vol[v], c->W, c->H, c->Wp, c->d_begin, c->d_count, peers);
+        wta_scatter_kernel<<<grd, blk, 0, c->stream>>>(c->vol[v], c->W, c->H, c->Wp, c->d_begin, c->d_count, peers);
         PSM_LAUNCH_CHECK(c);
     }
     return stage_end(c, 3);
 }
 
-int psm_disp_reduce_p2p(psm_ctx* c, uint8_t* left, size_t left_step, uint8_t* right, size_t right_step)
+int psm_disp_reduce_p2p(psm_ctx* c)
 {
     if (int rc = bind(c)) return rc;
-    if (!c->p2p_own) return fail(c, PSM_ESTATE, "no gather buffer");
-    const size_t npix = (size_t)c->W * c->H;
+    if (!c->p2p_own || !c->p2p_peer[0]) return fail(c, PSM_ESTATE, "no exchange block");
+    const unsigned npix = (unsigned)((size_t)c->W * c->H);
     for (int v = 0; v < 2; ++v) {
-        const unsigned long long* g = c->p2p_own + ((size_t)c->p2p_parity * 2 + v) * c->p2p_nranks * npix;
-        keys_reduce_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, c->stream>>>(g, c->p2p_nranks, npix, c->dis[v]);
+        P2pPeers peers;
+        p2p_fill(c, v, peers);
+        chunk_reduce_kernel<<<(peers.chunk + 255) / 256, 256, 0, c->stream>>>(peers, npix);
         PSM_LAUNCH_CHECK(c);
     }
-    if (left && right) {
-        if (int rc = copy_map_out(c, c->dis[0], left, left_step)) return rc;
-        if (int rc = copy_map_out(c, c->dis[1], right, right_step)) return rc;
-    }
+    return PSM_OK;
+}
+
+int psm_disp_fetch_p2p(psm_ctx* c, uint8_t* left, size_t left_step, uint8_t* right, size_t right_step)
+{
+    if (int rc = bind(c)) return rc;
+    if (!c->p2p_own) return fail(c, PSM_ESTATE, "no exchange block");
+    const unsigned char* maps = c->p2p_own + p2p_keys_bytes(c, c->p2p_nranks);
+    if (int rc = copy_map_out(c, maps, left, left_step)) return rc;
+    if (int rc = copy_map_out(c, maps + (size_t)c->W * c->H, right, right_step)) return rc;
     PSM_CUDA(c, cudaStreamSynchronize(c->stream));
     return PSM_OK;
 }

@@ -465,16 +465,24 @@ __global__ void __launch_bounds__(256) wta_kernel(const float* __restrict__ vol,
     }
 }
 
-// WTA fused with the all-gather of the sharded path: the same scan as wta_kernel, but the packed
-// (cost,d) minimum of every pixel is stored into slot `rank` of EVERY rank's gather buffer -- peer
-// device memory mapped over NVLink -- so compute and exchange are one kernel.
+// Sharded WTA fused with its exchange (reduce-scatter + all-gather of a min-reduction, hand-rolled
+// over NVLink peer memory).  Pixels are partitioned into `nranks` chunks; rank r is the reducer of
+// chunk r.
+//   wta_scatter_kernel : the WTA scan of wta_kernel, then the packed (cost,d) minimum of every pixel
+//                        is stored into its reducer's exchange block, slot [this rank][pixel-in-chunk]
+//                        (peer device memory, plain st.global over NVLink) -- compute + scatter in one kernel;
+//   chunk_reduce_kernel: the reducer takes the min over the nranks slots of its chunk and stores the
+//                        winning disparity (u8) into EVERY rank's result map -- reduce + gather in one kernel.
+// A cross-rank barrier separates the two kernels and follows the second one.
 struct P2pPeers {
-    unsigned long long* buf[8];  // gather buffers [nranks][H*W] of this view and frame parity, per rank
+    unsigned long long* keys[8];  // per rank: exchange block of this view  [nranks][chunk]
+    unsigned char* maps[8];       // per rank: result map of this view       [H*W]
     int nranks, rank;
+    unsigned chunk;               // pixels per chunk (last chunk may be partly unused)
 };
 
-__global__ void __launch_bounds__(256) wta_p2p_kernel(const float* __restrict__ vol, int W, int H, int Wp, int d_begin, int d_count,
-                                                      P2pPeers peers)
+__global__ void __launch_bounds__(256) wta_scatter_kernel(const float* __restrict__ vol, int W, int H, int Wp, int d_begin, int d_count,
+                                                          P2pPeers peers)
 {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
@@ -493,21 +501,30 @@ __global__ void __launch_bounds__(256) wta_p2p_kernel(const float* __restrict__ 
         if (c.z < mc[2]) { mc[2] = c.z; md[2] = d; }
         if (c.w < mc[3]) { mc[3] = c.w; md[3] = d; }
     }
-    const size_t npix = (size_t)W * H;
-    const size_t base = (size_t)peers.rank * npix + (size_t)y * W + x4;
-    unsigned long long k[4];
+    const unsigned pix0 = (unsigned)y * (unsigned)W + (unsigned)x4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) k[j] = ((unsigned long long)float_order_key(mc[j]) << 32) | (unsigned)md[j];
-    for (int r = 0; r < peers.nranks; ++r) {
-        unsigned long long* dst = peers.buf[r] + base;  // peer (or own) memory
-        if (x4 + 3 < W && (((size_t)dst) & 15) == 0) {
-            reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(k[0], k[1]);
-            reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(k[2], k[3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if (x4 + j < W) dst[j] = k[j];
-        }
+    for (int j = 0; j < 4; ++j) {
+        if (x4 + j >= W) break;
+        const unsigned pix = pix0 + j;
+        const unsigned owner = pix / peers.chunk;
+        const unsigned long long key = ((unsigned long long)float_order_key(mc[j]) << 32) | (unsigned)md[j];
+        peers.keys[owner][(size_t)peers.rank * peers.chunk + (pix - owner * peers.chunk)] = key;  // peer (or own) memory
     }
+}
+
+__global__ void __launch_bounds__(256) chunk_reduce_kernel(P2pPeers peers, unsigned npix)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;   // pixel inside this rank's chunk
+    const unsigned pix = (unsigned)peers.rank * peers.chunk + i;
+    if (i >= peers.chunk || pix >= npix) return;
+    const unsigned long long* mine = peers.keys[peers.rank];
+    unsigned long long k = mine[i];
+    for (int r = 1; r < peers.nranks; ++r) {
+        const unsigned long long v = mine[(size_t)r * peers.chunk + i];
+        k = v < k ? v : k;
+    }
+    const unsigned char d = (unsigned char)(k & 0xffu);
+    for (int r = 0; r < peers.nranks; ++r) peers.maps[r][pix] = d;  // every rank receives the final map
 }
 
 // Final step of the sharded WTA: min over ranks of the packed keys, low 8 bits -> u8 map.

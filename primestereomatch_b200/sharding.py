@@ -36,11 +36,11 @@ def gather_and_reduce(de, keys, gathered, world, lmap=None, rmap=None, group=Non
 
 
 class P2PExchange:
-    """WTA fused with its all-gather: each rank's WTA kernel stores its packed minima straight into
-    every rank's gather buffer over NVLink peer memory (psm_disp_select_keys_p2p).  Buffers are
-    shared between the per-GPU processes through CUDA IPC handles exchanged once at set-up.
-
-    Per frame: select() on every rank, one tiny barrier collective on the same stream, reduce()."""
+    """Sharded WTA fused with its exchange over NVLink peer memory (see include/prime_stereo_b200.h):
+    select() = WTA + scatter of packed minima into the reducers' blocks, reduce() = chunk min +
+    gather of the u8 result into every rank's map, fetch() = D2H.  barrier() (a 1-element NCCL
+    all-reduce on the current stream) must run between select/reduce and reduce/fetch.
+    Exchange blocks are shared between the per-GPU processes through CUDA IPC handles exchanged once."""
 
     def __init__(self, de, world, rank, group=None):
         import torch
@@ -74,6 +74,15 @@ class P2PExchange:
         import torch.distributed as dist
         dist.all_reduce(self._flag, group=self.group)  # stream-ordered cross-rank barrier
 
-    def reduce(self, lmap_ptr=None, rmap_ptr=None):
-        capi.check(capi.lib().psm_disp_reduce_p2p(self.de.handle, lmap_ptr, self.de.wid, rmap_ptr, self.de.wid),
+    def reduce(self):
+        capi.check(capi.lib().psm_disp_reduce_p2p(self.de.handle), self.de.handle)
+
+    def fetch(self, lmap_ptr, rmap_ptr):
+        capi.check(capi.lib().psm_disp_fetch_p2p(self.de.handle, lmap_ptr, self.de.wid, rmap_ptr, self.de.wid),
                    self.de.handle)
+
+    def frame(self, lmap_ptr=None, rmap_ptr=None):
+        """select -> barrier -> reduce -> barrier [-> fetch]"""
+        self.select(); self.barrier(); self.reduce(); self.barrier()
+        if lmap_ptr is not None:
+            self.fetch(lmap_ptr, rmap_ptr)

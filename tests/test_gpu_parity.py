@@ -284,9 +284,10 @@ def test_cpp_dispest_facade_demo(tmp_path, scenes, oracle_scene_results):
 
 
 def test_fused_wta_p2p_gather_matches_unsharded(scenes, oracle_scene_results):
-    """psm_disp_select_keys_p2p: the WTA kernel of each shard stores its packed minima into every
-    shard's gather buffer (here both buffers live on the one GPU; across processes they are peer
-    mappings).  Two frames exercise the parity double-buffering."""
+    """Fused WTA + exchange: each shard's WTA kernel scatters its packed minima into the exchange block
+    of the shard that reduces that pixel chunk; each reducer then writes the winning disparities into
+    every shard's result map (here all blocks live on the one GPU; across processes they are NVLink
+    peer mappings).  Two frames check that the blocks can be reused."""
     _, _, l, r = scenes["Teddy"]
     H, W, _ = l.shape
     L = capi.lib()
@@ -304,11 +305,15 @@ def test_fused_wta_p2p_gather_matches_unsharded(scenes, oracle_scene_results):
                 de.CostConst_GPU(); de.CostFilter_GPU()
                 capi.check(L.psm_disp_select_keys_p2p(de.handle), de.handle)
             for de in shards:
+                de.sync()                                   # stands in for the cross-rank barrier
+            for de in shards:
+                capi.check(L.psm_disp_reduce_p2p(de.handle), de.handle)
+            for de in shards:
                 de.sync()
             for de in shards:
                 ld = np.zeros((H, W), np.uint8); rd = np.zeros((H, W), np.uint8)
-                capi.check(L.psm_disp_reduce_p2p(de.handle, ld.ctypes.data_as(C.c_void_p), W,
-                                                 rd.ctypes.data_as(C.c_void_p), W), de.handle)
+                capi.check(L.psm_disp_fetch_p2p(de.handle, ld.ctypes.data_as(C.c_void_p), W,
+                                                rd.ctypes.data_as(C.c_void_p), W), de.handle)
                 assert_same(ld, oracle_scene_results["Teddy"]["ld"], f"p2p lDisMap frame {frame}")
                 assert_same(rd, oracle_scene_results["Teddy"]["rd"], f"p2p rDisMap frame {frame}")
     finally:
@@ -356,9 +361,13 @@ def test_c5_shape_sharded_eight_ways_on_one_gpu(oracle):
             capi.check(L.psm_disp_select_keys_p2p(de.handle), de.handle)
         for de in shards:
             de.sync()
+        for de in shards:
+            capi.check(L.psm_disp_reduce_p2p(de.handle), de.handle)
+        for de in shards:
+            de.sync()
         ld = np.zeros((H, W), np.uint8); rd = np.zeros((H, W), np.uint8)
-        capi.check(L.psm_disp_reduce_p2p(shards[3].handle, ld.ctypes.data_as(C.c_void_p), W,
-                                         rd.ctypes.data_as(C.c_void_p), W), shards[3].handle)
+        capi.check(L.psm_disp_fetch_p2p(shards[3].handle, ld.ctypes.data_as(C.c_void_p), W,
+                                        rd.ctypes.data_as(C.c_void_p), W), shards[3].handle)
         assert_same(ld, ref["lDis"], "8-way sharded lDisMap")
         assert_same(rd, ref["rDis"], "8-way sharded rDisMap")
     finally:
