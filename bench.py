@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seg-rows", type=int, default=0)
+    ap.add_argument("--extra-smem", type=int, default=0)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: p2p = WTA kernel stores its minima into every rank's buffer over NVLink (fused "
                          "compute+exchange); nccl = local WTA then ncclAllGather")
@@ -166,7 +167,10 @@ def main():
     warm = max(3, args.warmup)
 
     L = capi.lib()
-    l, r, _ = synth.stereo_pair_f32(W, H, D)
+    l8, r8, _ = synth.stereo_pair_u8(W, H, D)
+    l, r = synth.to_f32(l8), synth.to_f32(r8)
+    lp8 = torch.from_numpy(l8).pin_memory()
+    rp8 = torch.from_numpy(r8).pin_memory()
     lp = torch.from_numpy(l).pin_memory()
     rp = torch.from_numpy(r).pin_memory()
     ld_dev, rd_dev = lp.cuda(), rp.cuda()
@@ -180,6 +184,7 @@ def main():
     de.set_option(capi.PSM_OPT_CVF_MODE, args.cvf_mode)
     de.set_option(capi.PSM_OPT_VARIANT, args.variant)
     de.set_option(101, args.seg_rows)
+    de.set_option(102, args.extra_smem)
     stream = torch.cuda.Stream()  # a real (non-default) stream: handle 0 would mean "context's own stream"
     torch.cuda.set_stream(stream)
     capi.check(L.psm_set_stream(de.handle, C.c_void_p(stream.cuda_stream)), de.handle)
@@ -197,7 +202,9 @@ def main():
     step_bytes = W * 3 * 4
 
     def step(e2e):
-        if e2e:
+        if e2e == "u8":   # caller keeps 8-bit frames: StereoMatch.cpp:193-197's convertTo runs on the device
+            capi.check(L.psm_set_images_u8(de.handle, lp8.data_ptr(), W * 3, rp8.data_ptr(), W * 3), de.handle)
+        elif e2e:
             capi.check(L.psm_set_images(de.handle, lp.data_ptr(), step_bytes, rp.data_ptr(), step_bytes), de.handle)
         else:
             capi.check(L.psm_set_images_device(de.handle, ld_dev.data_ptr(), step_bytes, rd_dev.data_ptr(), step_bytes), de.handle)
@@ -262,6 +269,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     stage = {n: de.stage_ms(i) for i, n in enumerate(["ingest", "cvc", "cvf", "wta", "cvf_kernel"])}
     e2e_ms = timed(True, args.steps)
+    e2e_u8_ms = timed("u8", args.steps)
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -293,6 +301,9 @@ def main():
                          "peak_source": peak_src},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * W * H * 3 * 4 * world,
                     "d2h_bytes_per_step": 2 * W * H * world, "ms_per_step": e2e_ms / args.steps},
+            "e2e_u8": {"value": 1e3 / (e2e_u8_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": 2 * W * H * 3 * world,
+                       "d2h_bytes_per_step": 2 * W * H * world, "ms_per_step": e2e_u8_ms / args.steps,
+                       "note": "same as e2e but the host frames are 8-bit (psm_set_images_u8)"},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
         }

@@ -45,7 +45,7 @@ struct psm_ctx {
     size_t ab_slices = 0;
     cudaEvent_t ev0[kNumStages] = {}, ev1[kNumStages] = {};
     bool ev_valid[kNumStages] = {};
-    int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0, cvf_target_rows = 0;
+    int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0, cvf_target_rows = 0, cvf_extra_smem = 0;
     bool have_images = false, guide_valid = false, have_cvc = false;
     uint64_t launches = 0;
     char err[512] = "";
@@ -188,7 +188,7 @@ int launch_cvf_stream(psm_ctx* c)
     if (ctas_1seg * (c->H / 256 > 0 ? c->H / 256 : 1) < 148 * 3 * 4) target_rows = 128;
     if (c->cvf_target_rows > 0) target_rows = c->cvf_target_rows;
     plan_segments(c->H, target_rows, &P.nseg, &P.seg_rows);
-    const size_t smem = (size_t)8 * 4 * kCvfThreads * sizeof(float4);
+    const size_t smem = (size_t)8 * 4 * kCvfThreads * sizeof(float4) + (size_t)c->cvf_extra_smem;
     if (!c->cvf_attr_set) {
         PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -341,6 +341,10 @@ int psm_set_option(psm_ctx* c, int key, int value)
         return PSM_OK;
     case 100:  // undocumented: streaming-kernel variant selector for tuning experiments
         c->cvf_variant = value;
+        return PSM_OK;
+    case 102:  // undocumented: extra dynamic shared memory per CTA (bytes) to throttle occupancy in experiments
+        c->cvf_extra_smem = value;
+        c->cvf_attr_set = false;
         return PSM_OK;
     case 101:  // undocumented: rows per segment of the streaming kernel (0 = automatic)
         c->cvf_target_rows = value;
