@@ -29,7 +29,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, D = 1920, 1080, 128
+WORKLOADS = {  # BASELINE.json configs; C4 is the one the metric is quoted on and the default at every N
+    "C3": (1280, 720, 64), "C4": (1920, 1080, 128), "C5": (1920, 1080, 256),
+}
+W, H, D = WORKLOADS["C4"]
 WORKLOAD = "C4 synthetic 1920x1080 D=128 fp32, both views (lDisMap+rDisMap)"
 METRIC = "disparity_volumes_per_s"
 UNIT = "volumes/s"
@@ -139,12 +142,17 @@ def main():
     ap.add_argument("--cvf-mode", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS),
+                    help="C4 (default) is the benchmark; C3 / C5 are the other synthetic BASELINE configs")
     ap.add_argument("--seg-rows", type=int, default=0)
     ap.add_argument("--extra-smem", type=int, default=0)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: p2p = WTA kernel stores its minima into every rank's buffer over NVLink (fused "
                          "compute+exchange); nccl = local WTA then ncclAllGather")
     args = ap.parse_args()
+    global W, H, D, WORKLOAD
+    W, H, D = WORKLOADS[args.workload]
+    WORKLOAD = f"{args.workload} synthetic {W}x{H} D={D} fp32, both views (lDisMap+rDisMap)"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -66,10 +66,6 @@ __device__ __forceinline__ f2x2 sub2(const f2x2& a, const f2x2& b)
 {
     return {make_float2(fsub(a.lo.x, b.lo.x), fsub(a.lo.y, b.lo.y)), make_float2(fsub(a.hi.x, b.hi.x), fsub(a.hi.y, b.hi.y))};
 }
-template <int J> __device__ __forceinline__ float get(const f2x2& v)
-{
-    return J == 0 ? v.lo.x : (J == 1 ? v.lo.y : (J == 2 ? v.hi.x : v.hi.y));
-}
 __device__ __forceinline__ float get(const f2x2& v, int j) { return j == 0 ? v.lo.x : (j == 1 ? v.lo.y : (j == 2 ? v.hi.x : v.hi.y)); }
 
 // f32 -> f64 without the conversion pipe: for a positive normal float the double is
