@@ -13,6 +13,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the built artefacts are git-ignored: on a fresh checkout compile them once (nvcc cross-compiles
+    # sm_100a without a GPU; the oracle is plain gcc)
+    lib = os.path.join(ROOT, "primestereomatch_b200", "libprime_stereo_b200.so")
+    orc = os.path.join(ROOT, "oracle", "libstereo_oracle.so")
+    if not (os.path.exists(lib) and os.path.exists(orc)):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def read_png(path, gray=False):

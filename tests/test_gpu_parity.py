@@ -373,3 +373,27 @@ def test_c5_shape_sharded_eight_ways_on_one_gpu(oracle):
     finally:
         for de in shards:
             de.close()
+
+
+def test_row_steps_like_cv_mat_rois(scenes, oracle_scene_results):
+    """cv::Mat inputs/outputs may have row steps larger than the packed width (ROIs, aligned
+    allocations): psm_set_images / psm_disp_select honour the byte steps."""
+    _, _, l, r = scenes["Teddy"]
+    H, W, _ = l.shape
+    L = capi.lib()
+    lp = np.full((H, W + 37, 3), np.nan, np.float32); lp[:, :W] = l      # padded rows, NaN in the padding
+    rp = np.full((H, W + 5, 3), np.nan, np.float32); rp[:, :W] = r
+    ld = np.full((H, W + 11), 255, np.uint8); rd = np.full((H, W + 64), 255, np.uint8)
+    with DispEst(l, r, 64) as de:
+        capi.check(L.psm_set_images(de.handle, lp.ctypes.data_as(C.c_void_p), lp.strides[0],
+                                    rp.ctypes.data_as(C.c_void_p), rp.strides[0]), de.handle)
+        capi.check(L.psm_cost_const(de.handle), de.handle)
+        capi.check(L.psm_cost_filter(de.handle), de.handle)
+        capi.check(L.psm_disp_select(de.handle, ld.ctypes.data_as(C.c_void_p), ld.strides[0],
+                                     rd.ctypes.data_as(C.c_void_p), rd.strides[0]), de.handle)
+        # a step smaller than one packed row is rejected
+        assert L.psm_set_images(de.handle, lp.ctypes.data_as(C.c_void_p), W * 12 - 4,
+                                rp.ctypes.data_as(C.c_void_p), rp.strides[0]) == capi.PSM_EINVAL
+    assert_same(ld[:, :W], oracle_scene_results["Teddy"]["ld"], "lDisMap with row steps")
+    assert_same(rd[:, :W], oracle_scene_results["Teddy"]["rd"], "rDisMap with row steps")
+    assert np.all(ld[:, W:] == 255) and np.all(rd[:, W:] == 255)  # padding untouched
