@@ -486,14 +486,14 @@ __global__ void __launch_bounds__(256) wta_scatter_kernel(const float* __restric
 {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
-    if (x4 >= W) return;
+    const bool active = x4 < W;  // inactive lanes still take part in the staged store below
     const size_t plane = (size_t)H * Wp;
-    const float* p = vol + (size_t)y * Wp + x4;
+    const float* p = vol + (size_t)y * Wp + (active ? x4 : 0);
     float mc[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
     int md[4] = {0, 0, 0, 0};
     int dl = (d_begin == 0) ? 1 : 0;
 #pragma unroll 8
-    for (; dl < d_count; ++dl) {
+    for (; active && dl < d_count; ++dl) {
         const float4 c = __ldg(reinterpret_cast<const float4*>(p + (size_t)dl * plane));
         const int d = d_begin + dl;
         if (c.x < mc[0]) { mc[0] = c.x; md[0] = d; }
@@ -501,14 +501,25 @@ __global__ void __launch_bounds__(256) wta_scatter_kernel(const float* __restric
         if (c.z < mc[2]) { mc[2] = c.z; md[2] = d; }
         if (c.w < mc[3]) { mc[3] = c.w; md[3] = d; }
     }
-    const unsigned pix0 = (unsigned)y * (unsigned)W + (unsigned)x4;
+    // Stage the warp's 128 keys in shared memory and send them out lane-contiguously: every store
+    // instruction then writes 32 consecutive keys (256 contiguous bytes, whole 32-byte sectors) to
+    // one peer, instead of 32 lanes x 8 bytes at a 32-byte stride (partial sectors over NVLink).
+    __shared__ unsigned long long stage[8][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (x4 + j >= W) break;
-        const unsigned pix = pix0 + j;
-        const unsigned owner = pix / peers.chunk;
-        const unsigned long long key = ((unsigned long long)float_order_key(mc[j]) << 32) | (unsigned)md[j];
-        peers.keys[owner][(size_t)peers.rank * peers.chunk + (pix - owner * peers.chunk)] = key;  // peer (or own) memory
+    for (int j = 0; j < 4; ++j)
+        stage[warp][4 * lane + j] = ((unsigned long long)float_order_key(mc[j]) << 32) | (unsigned)md[j];
+    __syncwarp();
+    const int xw = x4 - 4 * lane;  // first column of this warp
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+        const int idx = 32 * s4 + lane;
+        const int x = xw + idx;
+        if (x < W) {
+            const unsigned pix = (unsigned)y * (unsigned)W + (unsigned)x;
+            const unsigned owner = pix / peers.chunk;
+            peers.keys[owner][(size_t)peers.rank * peers.chunk + (pix - owner * peers.chunk)] = stage[warp][idx];  // peer (or own) memory
+        }
     }
 }
 
