@@ -146,6 +146,7 @@ def main():
                     help="C4 (default) is the benchmark; C3 / C5 are the other synthetic BASELINE configs")
     ap.add_argument("--seg-rows", type=int, default=0)
     ap.add_argument("--extra-smem", type=int, default=0)
+    ap.add_argument("--cta-threads", type=int, default=0)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: p2p = WTA kernel stores its minima into every rank's buffer over NVLink (fused "
                          "compute+exchange); nccl = local WTA then ncclAllGather")
@@ -193,6 +194,7 @@ def main():
     de.set_option(capi.PSM_OPT_VARIANT, args.variant)
     de.set_option(101, args.seg_rows)
     de.set_option(102, args.extra_smem)
+    de.set_option(103, args.cta_threads)
     stream = torch.cuda.Stream()  # a real (non-default) stream: handle 0 would mean "context's own stream"
     torch.cuda.set_stream(stream)
     capi.check(L.psm_set_stream(de.handle, C.c_void_p(stream.cuda_stream)), de.handle)

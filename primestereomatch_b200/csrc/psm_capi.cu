@@ -45,7 +45,7 @@ struct psm_ctx {
     size_t ab_slices = 0;
     cudaEvent_t ev0[kNumStages] = {}, ev1[kNumStages] = {};
     bool ev_valid[kNumStages] = {};
-    int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0, cvf_target_rows = 0, cvf_extra_smem = 0;
+    int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0, cvf_target_rows = 0, cvf_extra_smem = 0, cvf_threads = 0;
     bool have_images = false, guide_valid = false, have_cvc = false;
     uint64_t launches = 0;
     char err[512] = "";
@@ -180,7 +180,9 @@ int launch_cvf_stream(psm_ctx* c)
     for (int v = 0; v < 2; ++v) { P.vol_in[v] = c->vol[v]; P.vol_out[v] = c->vol_alt[v]; P.guide[v] = c->guide[v]; }
     P.W = c->W; P.H = c->H; P.Wp = c->Wp; P.Dloc = c->d_count;
     P.nstrips = (c->W + kStripOut - 1) / kStripOut;
-    P.ndgroups = (c->d_count + 3) / 4;
+    const int nthreads = c->cvf_threads > 0 ? c->cvf_threads : kCvfThreads;
+    const int wpc = nthreads / 32;
+    P.ndgroups = (c->d_count + wpc - 1) / wpc;
     // enough CTAs for several waves over 148 SMs x 3 resident CTAs, but segments no shorter than
     // ~128 rows (each segment pays ~11 warm-up rows)
     int target_rows = 256;
@@ -188,7 +190,7 @@ int launch_cvf_stream(psm_ctx* c)
     if (ctas_1seg * (c->H / 256 > 0 ? c->H / 256 : 1) < 148 * 3 * 4) target_rows = 128;
     if (c->cvf_target_rows > 0) target_rows = c->cvf_target_rows;
     plan_segments(c->H, target_rows, &P.nseg, &P.seg_rows);
-    const size_t smem = (size_t)8 * 4 * kCvfThreads * sizeof(float4) + (size_t)c->cvf_extra_smem;
+    const size_t smem = (size_t)8 * 4 * nthreads * sizeof(float4) + (size_t)c->cvf_extra_smem;
     if (!c->cvf_attr_set) {
         PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -198,10 +200,10 @@ int launch_cvf_stream(psm_ctx* c)
     }
     const unsigned grid = 2u * P.nseg * P.nstrips * P.ndgroups;
     switch (c->cvf_variant) {  // tuning variants (PSM option 100); 0 is the shipped default
-    case 1: cvf_stream_kernel<2, 0><<<grid, kCvfThreads, smem, c->stream>>>(P); break;
-    case 2: cvf_stream_kernel<3, 1><<<grid, kCvfThreads, smem, c->stream>>>(P); break;
-    case 3: cvf_stream_kernel<3, 2><<<grid, kCvfThreads, smem, c->stream>>>(P); break;
-    default: cvf_stream_kernel<3, 0><<<grid, kCvfThreads, smem, c->stream>>>(P); break;
+    case 1: cvf_stream_kernel<2, 0><<<grid, nthreads, smem, c->stream>>>(P); break;
+    case 2: cvf_stream_kernel<3, 1><<<grid, nthreads, smem, c->stream>>>(P); break;
+    case 3: cvf_stream_kernel<3, 2><<<grid, nthreads, smem, c->stream>>>(P); break;
+    default: cvf_stream_kernel<3, 0><<<grid, nthreads, smem, c->stream>>>(P); break;
     }
     PSM_LAUNCH_CHECK(c);
     return PSM_OK;
@@ -341,6 +343,11 @@ int psm_set_option(psm_ctx* c, int key, int value)
         return PSM_OK;
     case 100:  // undocumented: streaming-kernel variant selector for tuning experiments
         c->cvf_variant = value;
+        return PSM_OK;
+    case 103:  // undocumented: threads per CTA of the streaming kernel (64 / 96 / 128)
+        if (value != 0 && (value % 32 != 0 || value < 32 || value > 128)) return fail(c, PSM_EINVAL, "bad thread count");
+        c->cvf_threads = value;
+        c->cvf_attr_set = false;
         return PSM_OK;
     case 102:  // undocumented: extra dynamic shared memory per CTA (bytes) to throttle occupancy in experiments
         c->cvf_extra_smem = value;

@@ -17,7 +17,7 @@
 // Work decomposition (B200-first; nothing like the reference's per-slice Mat pipeline):
 //   warp   = one strip of 128 input columns (112 output columns) of ONE disparity slice, one row segment
 //   lane   = 4 consecutive columns -> every global access is a 128-bit load/store
-//   CTA    = 4 warps = 4 consecutive slices of the same strip and segment (guide rows hit in L1)
+//   CTA    = 3 warps = 3 consecutive slices of the same strip and segment (guide rows hit in L1)
 //   stage 1: S1[4 boxes][4 cols] fp64 running column sums of p, I0*p, I1*p, I2*p;
 //            row sums = per-lane prefix/suffix sums + 4 fp64 shuffles per box (lane+1 total, lane+2 prefixes)
 //   a,b    : CVF.cpp:92-155 with the d-independent adjugate / 1/det precomputed per pixel (K2)
@@ -44,7 +44,8 @@ namespace psm {
 
 constexpr int kStripOut = 112;  // output columns per warp
 constexpr int kStripIn = 128;   // input columns per warp
-constexpr int kCvfThreads = 128;
+constexpr int kCvfThreads = 96;       // shipped CTA size: 3 slice-warps, 48 KB ring, 4 CTAs/SM (measured best of 32/64/96/128)
+constexpr int kCvfMaxThreads = 128;   // upper bound the register allocation is sized for
 
 struct CvfParams {
     const float* vol_in[2];   // raw volumes  [Dloc][H][Wp]   (pointer to row 0, column 0)
@@ -89,22 +90,23 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 // MINB: resident CTAs per SM the register allocation is sized for (3 -> <=168 regs, 2 -> <=255);
 // IW: integer widening (widen_pos) of the stage-1 inputs: 0 none, 1 oldest rows, 2 newest + oldest rows.
 template <int MINB, int IW>
-__global__ void __launch_bounds__(kCvfThreads, MINB)
+__global__ void __launch_bounds__(kCvfMaxThreads, MINB)
 cvf_stream_kernel(const CvfParams P)
 {
-    extern __shared__ float4 ring[];  // [8 slots][4 planes][128 threads]
+    extern __shared__ float4 ring[];  // [8 slots][4 planes][blockDim.x threads]
     constexpr bool IWN = IW >= 2, IWO = IW >= 1;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    constexpr int nthr = kCvfThreads;
+    const int nthr = blockDim.x;            // kCvfThreads in the shipped configuration (option 103 varies it)
+    const int wpc = nthr >> 5;
 
     int b = blockIdx.x;
     const int dgroup = b % P.ndgroups; b /= P.ndgroups;
     const int strip = b % P.nstrips;   b /= P.nstrips;
     const int seg = b % P.nseg;
     const int view = b / P.nseg;
-    const bool slice_ok = dgroup * 4 + warp < P.Dloc;
-    const int dlc = slice_ok ? dgroup * 4 + warp : P.Dloc - 1;  // surplus warps redo the last slice, stores masked
+    const bool slice_ok = dgroup * wpc + warp < P.Dloc;
+    const int dlc = slice_ok ? dgroup * wpc + warp : P.Dloc - 1;  // surplus warps redo the last slice, stores masked
     if (!slice_ok) return;  // warps never synchronise with each other
 
     const int W = P.W, H = P.H;
