@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--seg-rows", type=int, default=0)
     ap.add_argument("--extra-smem", type=int, default=0)
     ap.add_argument("--cta-threads", type=int, default=0)
+    ap.add_argument("--remap", type=int, default=0)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: p2p = WTA kernel stores its minima into every rank's buffer over NVLink (fused "
                          "compute+exchange); nccl = local WTA then ncclAllGather")
@@ -195,6 +196,7 @@ def main():
     de.set_option(101, args.seg_rows)
     de.set_option(102, args.extra_smem)
     de.set_option(103, args.cta_threads)
+    de.set_option(104, args.remap)
     stream = torch.cuda.Stream()  # a real (non-default) stream: handle 0 would mean "context's own stream"
     torch.cuda.set_stream(stream)
     capi.check(L.psm_set_stream(de.handle, C.c_void_p(stream.cuda_stream)), de.handle)

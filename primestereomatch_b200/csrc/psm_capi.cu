@@ -45,7 +45,7 @@ struct psm_ctx {
     size_t ab_slices = 0;
     cudaEvent_t ev0[kNumStages] = {}, ev1[kNumStages] = {};
     bool ev_valid[kNumStages] = {};
-    int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0, cvf_target_rows = 0, cvf_extra_smem = 0, cvf_threads = 0;
+    int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0, cvf_target_rows = 0, cvf_extra_smem = 0, cvf_threads = 0, cvf_remap = 0;
     bool have_images = false, guide_valid = false, have_cvc = false;
     uint64_t launches = 0;
     char err[512] = "";
@@ -188,6 +188,14 @@ int launch_cvf_stream(psm_ctx* c)
     int target_rows = 256;
     const long ctas_1seg = 2L * P.nstrips * P.ndgroups;
     if (ctas_1seg * (c->H / 256 > 0 ? c->H / 256 : 1) < 148 * 3 * 4) target_rows = 128;
+    P.remap_sms = 0; P.remap_ctas = 0;
+    if (c->cvf_remap) {
+        int nsm = 0;
+        PSM_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
+        P.remap_sms = nsm;
+        P.remap_ctas = (int)((227 * 1024) / ((size_t)8 * 4 * nthreads * sizeof(float4) + 1024));  // resident CTAs by shared memory
+        if (P.remap_ctas * nthreads * 170 > 65536) P.remap_ctas = 65536 / (nthreads * 170);      // ... and by registers
+    }
     if (c->cvf_target_rows > 0) target_rows = c->cvf_target_rows;
     plan_segments(c->H, target_rows, &P.nseg, &P.seg_rows);
     const size_t smem = (size_t)8 * 4 * nthreads * sizeof(float4) + (size_t)c->cvf_extra_smem;
@@ -343,6 +351,9 @@ int psm_set_option(psm_ctx* c, int key, int value)
         return PSM_OK;
     case 100:  // undocumented: streaming-kernel variant selector for tuning experiments
         c->cvf_variant = value;
+        return PSM_OK;
+    case 104:  // undocumented: block->work remap so that co-resident CTAs are work neighbours (0/1)
+        c->cvf_remap = value;
         return PSM_OK;
     case 103:  // undocumented: threads per CTA of the streaming kernel (64 / 96 / 128)
         if (value != 0 && (value % 32 != 0 || value < 32 || value > 128)) return fail(c, PSM_EINVAL, "bad thread count");

@@ -53,6 +53,7 @@ struct CvfParams {
     const float* guide[2];    // guide planes [kGuidePlanes][H][Wp]
     int W, H, Wp, Dloc;
     int nstrips, nseg, seg_rows, ndgroups;
+    int remap_sms, remap_ctas;  // SM count and resident CTAs per SM for the block->work remap (0: identity)
 };
 
 struct f2x2 { float2 lo, hi; };  // four columns as two packed pairs
@@ -100,7 +101,15 @@ cvf_stream_kernel(const CvfParams P)
     const int nthr = blockDim.x;            // kCvfThreads in the shipped configuration (option 103 varies it)
     const int wpc = nthr >> 5;
 
+    // Block -> work mapping.  Hardware hands consecutive blockIdx to consecutive SMs, so the CTAs that
+    // share an SM (and its L1) are blockIdx k, k+nsm, k+2nsm, ...; the remap makes those neighbours in
+    // work order (consecutive slice groups of the same strip and segment), which read the same guide rows.
     int b = blockIdx.x;
+    if (P.remap_sms > 0) {
+        const int per = P.remap_sms * P.remap_ctas;
+        const int chunk = b / per, r = b - chunk * per;
+        if ((chunk + 1) * per <= (int)gridDim.x) b = chunk * per + (r % P.remap_sms) * P.remap_ctas + r / P.remap_sms;
+    }
     const int dgroup = b % P.ndgroups; b /= P.ndgroups;
     const int strip = b % P.nstrips;   b /= P.nstrips;
     const int seg = b % P.nseg;
