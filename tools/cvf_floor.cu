@@ -15,7 +15,17 @@ __device__ __forceinline__ void hsum8(const double c[4], double h[4])
     h[0] = Tt + Tn; h[1] = (S3 + Tn) + Q1; h[2] = (S2 + Tn) + Q2; h[3] = (S1 + Tn) + Q3;
 }
 
-__global__ void __launch_bounds__(128, 3) floor_kernel(float* out, const float* in, int rows, long long* cyc)
+__device__ __forceinline__ double widen_pos(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    double d = __hiloint2double((int)((u >> 3) + 0x38000000u), (int)(u << 29));
+    if (u - 0x00800000u >= 0x7f000000u) d = (double)f;
+    return d;
+}
+template <int IW> __device__ __forceinline__ double wid(float f) { return IW ? widen_pos(f) : (double)f; }
+
+template <int MAXT, int MINB, int IW>
+__global__ void __launch_bounds__(MAXT, MINB) floor_kernel(float* out, const float* in, int rows, long long* cyc)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     float x[4][4], g[10][4];
@@ -29,7 +39,7 @@ __global__ void __launch_bounds__(128, 3) floor_kernel(float* out, const float* 
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) S1[q][j] = __dadd_rn(S1[q][j], (double)__fmul_rn(x[q][j], g[q][j]));      // widen newest
+            for (int j = 0; j < 4; ++j) S1[q][j] = __dadd_rn(S1[q][j], wid<IW>(__fmul_rn(x[q][j], g[q][j])));      // widen newest
         float m[4][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) { double h[4]; hsum8(S1[q], h);
@@ -38,7 +48,7 @@ __global__ void __launch_bounds__(128, 3) floor_kernel(float* out, const float* 
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) S1[q][j] = __dsub_rn(S1[q][j], (double)__fmul_rn(x[q][j], g[q + 4][j]));  // widen oldest
+            for (int j = 0; j < 4; ++j) S1[q][j] = __dsub_rn(S1[q][j], wid<IW>(__fmul_rn(x[q][j], g[q + 4][j])));  // widen oldest
 #pragma unroll
         for (int j = 0; j < 4; ++j) {  // cov, a, b: 33 fp32 ops per column
             const float c0 = __fsub_rn(m[1][j], __fmul_rn(g[0][j], m[0][j])), c1 = __fsub_rn(m[2][j], __fmul_rn(g[1][j], m[0][j])), c2 = __fsub_rn(m[3][j], __fmul_rn(g[2][j], m[0][j]));
@@ -71,24 +81,36 @@ __global__ void __launch_bounds__(128, 3) floor_kernel(float* out, const float* 
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-int main()
+template <int MAXT, int MINB, int IW>
+void run(const char* name, int threads, int ctas_per_sm, size_t smem)
 {
     int nsm; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
-    const int rows = 2000, threads = 96, ctas = nsm * 4;
+    const int rows = 2000, ctas = nsm * ctas_per_sm;
     float *out, *in; long long* cyc;
     cudaMalloc(&out, (size_t)ctas * threads * 4); cudaMalloc(&in, 4096); cudaMalloc(&cyc, ctas * 8);
     float h[1024]; for (int i = 0; i < 1024; ++i) h[i] = 0.25f + 0.001f * i;
     cudaMemcpy(in, h, 4096, cudaMemcpyHostToDevice);
-    cudaFuncSetAttribute(floor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152);
-    for (int it = 0; it < 2; ++it) floor_kernel<<<ctas, threads, 49152>>>(out, in, rows, cyc);  // 48 KB dynamic smem: same 4 CTAs/SM as the real kernel
+    auto k = floor_kernel<MAXT, MINB, IW>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int it = 0; it < 2; ++it) k<<<ctas, threads, smem>>>(out, in, rows, cyc);
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    cudaEventRecord(a); floor_kernel<<<ctas, threads, 49152>>>(out, in, rows, cyc); cudaEventRecord(b); cudaDeviceSynchronize();
+    cudaEventRecord(a); k<<<ctas, threads, smem>>>(out, in, rows, cyc); cudaEventRecord(b); cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, a, b);
-    printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
-    // warp-rows per SM = 4 CTAs * 3 warps * rows; cycles per warp-row per SM:
-    const double clk = ms * 1e-3 * 1.93e9;
-    printf("floor kernel: %.3f ms for %d rows x 12 warps/SM -> %.1f SM-cycles per warp-row (at 1.93 GHz)\n", ms, rows, clk / (12.0 * rows));
-    printf("C4 has 2*18*128*(1080+4*11) = %.0f warp-rows -> %.0f per SM -> floor %.2f ms\n", 2.0 * 18 * 128 * 1124, 2.0 * 18 * 128 * 1124 / nsm,
-           2.0 * 18 * 128 * 1124 / nsm * (clk / (12.0 * rows)) / 1.93e9 * 1e3);
+    const double warps = ctas_per_sm * threads / 32.0, clk = ms * 1e-3 * 1.93e9, per = clk / (warps * rows);
+    printf("%-34s warps/SM=%4.0f  %7.1f SM-cycles per warp-row -> C4 floor %.2f ms   (%s)\n", name, warps, per,
+           2.0 * 18 * 128 * 1124 / nsm * per / 1.93e9 * 1e3, cudaGetErrorString(cudaGetLastError()));
+    cudaFree(out); cudaFree(in); cudaFree(cyc);
+}
+
+int main()
+{
+    run<128, 3, 0>("shipped mix, 4x96 thr", 96, 4, 49152);
+    run<128, 3, 0>("shipped mix, 3x128 thr", 128, 3, 65536);
+    run<128, 3, 0>("shipped mix, 2x96 thr (6 warps)", 96, 2, 98304);
+    run<128, 4, 0>("<=128 regs, 4x128 thr (16 warps)", 128, 4, 32768);
+    run<128, 4, 0>("<=128 regs, 5x96 thr (15 warps)", 96, 5, 40000);
+    run<256, 2, 0>("<=128 regs, 2x256 thr (16 warps)", 256, 2, 65536);
+    run<128, 3, 1>("int widening stage 1, 4x96 thr", 96, 4, 49152);
+    run<128, 4, 1>("int widening, <=128 regs 16 warps", 128, 4, 32768);
     return 0;
 }
