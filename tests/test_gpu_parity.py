@@ -397,3 +397,23 @@ def test_row_steps_like_cv_mat_rois(scenes, oracle_scene_results):
     assert_same(ld[:, :W], oracle_scene_results["Teddy"]["ld"], "lDisMap with row steps")
     assert_same(rd[:, :W], oracle_scene_results["Teddy"]["rd"], "rDisMap with row steps")
     assert np.all(ld[:, W:] == 255) and np.all(rd[:, W:] == 255)  # padding untouched
+
+
+@pytest.mark.parametrize("lo,hi", [(-12, 3), (-40, 10)])
+def test_wide_dynamic_range_costs_stay_bit_exact(lo, hi, oracle):
+    """fp64 running sums are exact only while a window spans < 2^23 in magnitude; beyond that both
+    OpenCV's order and ours round in fp64 (differently).  The final rounding to float hides those
+    2^-53 effects except with probability ~2^-28 per mean, so even costs spanning e^50 must come out
+    bit-identical here."""
+    rng = np.random.default_rng(5)
+    H, W, D = 96, 256, 4
+    l = rng.random((H, W, 3), dtype=np.float32)
+    rgb, mean, var = oracle.cvf_preprocess(l)
+    vol = (np.abs(rng.standard_normal((D, H, W))) * np.exp(rng.uniform(lo, hi, (D, H, W)))).astype(np.float32)
+    want = np.stack([oracle.guided_filter(rgb, mean, var, vol[d]) for d in range(D)])
+    with DispEst(l, l, D) as de:
+        de.CostConst_GPU()
+        for d in range(D):
+            de.write_cost_slice(0, d, vol[d]); de.write_cost_slice(1, d, vol[d])
+        de.CostFilter_GPU()
+        assert_same(de.read_cost_volume(0), want, f"filtered volume, cost range e^{lo}..e^{hi}")

@@ -100,3 +100,28 @@ def test_bad_pixel_metric_matches_golden(golden, oracle_scene_results):
         e = cv2.multiply(e, occl, scale=1 / 255.0)
         bp = float(np.count_nonzero(e)) * 100.0 / gt.size
         assert abs(bp - golden["scenes"][scene]["bp_nonocc_left"]) < 1e-9
+
+
+def test_box_filter_matches_cv2_on_random_shapes_and_ranges(oracle):
+    """Property test of the one primitive everything hangs on: cv::boxFilter(f32, 8x8) == the oracle's
+    RowSum/ColumnSum restatement, on many shapes (incl. smaller than the window) and value ranges
+    (wide dynamic range, exact zeros, negatives, denormals)."""
+    cv2 = pytest.importorskip("cv2")
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 70), st.integers(1, 70), st.integers(0, 2**31 - 1), st.sampled_from(["unit", "wide", "sparse", "tiny"]))
+    def check(h, w, seed, kind):
+        rng = np.random.default_rng(seed)
+        if kind == "unit":
+            p = rng.random((h, w), dtype=np.float32)
+        elif kind == "wide":
+            p = (rng.standard_normal((h, w)) * np.exp(rng.uniform(-20, 10, (h, w)))).astype(np.float32)
+        elif kind == "sparse":
+            p = (rng.random((h, w)) * (rng.random((h, w)) < 0.2)).astype(np.float32)
+        else:
+            p = (rng.standard_normal((h, w)) * 1e-41).astype(np.float32)  # denormals
+        assert np.array_equal(oracle.box8(p), cv2.boxFilter(p, -1, (8, 8)))
+
+    check()
