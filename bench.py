@@ -148,6 +148,9 @@ def main():
     ap.add_argument("--extra-smem", type=int, default=0)
     ap.add_argument("--cta-threads", type=int, default=0)
     ap.add_argument("--remap", type=int, default=0)
+    ap.add_argument("--upload", default="banded", choices=["banded", "replicated"],
+                    help="N>1, e2e: banded = every rank uploads H/N rows of both images and the bands are "
+                         "all-gathered over NVLink; replicated = every rank uploads both full images over PCIe")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: p2p = WTA kernel stores its minima into every rank's buffer over NVLink (fused "
                          "compute+exchange); nccl = local WTA then ncclAllGather")
@@ -212,10 +215,25 @@ def main():
         from primestereomatch_b200.sharding import P2PExchange
         p2p = P2PExchange(de, world, rank)
     step_bytes = W * 3 * 4
+    banded = world > 1 and args.upload == "banded"
+    if banded:  # row band of this rank (pinned host views) + device buffers for the band and the gathered images
+        rows = (H + world - 1) // world
+        r0, r1 = min(H, rank * rows), min(H, (rank + 1) * rows)
+        band_l = torch.zeros((rows, W, 3), dtype=torch.float32, device="cuda")
+        band_r = torch.zeros((rows, W, 3), dtype=torch.float32, device="cuda")
+        full_l = torch.empty((world * rows, W, 3), dtype=torch.float32, device="cuda")
+        full_r = torch.empty((world * rows, W, 3), dtype=torch.float32, device="cuda")
 
     def step(e2e):
         if e2e == "u8":   # caller keeps 8-bit frames: StereoMatch.cpp:193-197's convertTo runs on the device
             capi.check(L.psm_set_images_u8(de.handle, lp8.data_ptr(), W * 3, rp8.data_ptr(), W * 3), de.handle)
+        elif e2e and banded:
+            # each rank moves only its band over PCIe; NVLink all-gather completes the images on every GPU
+            band_l[: r1 - r0].copy_(lp[r0:r1], non_blocking=True)
+            band_r[: r1 - r0].copy_(rp[r0:r1], non_blocking=True)
+            dist.all_gather_into_tensor(full_l.view(-1), band_l.view(-1))
+            dist.all_gather_into_tensor(full_r.view(-1), band_r.view(-1))
+            capi.check(L.psm_set_images_device(de.handle, full_l.data_ptr(), step_bytes, full_r.data_ptr(), step_bytes), de.handle)
         elif e2e:
             capi.check(L.psm_set_images(de.handle, lp.data_ptr(), step_bytes, rp.data_ptr(), step_bytes), de.handle)
         else:
@@ -311,7 +329,9 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_ms,
                          "peak_source": peak_src},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * W * H * 3 * 4 * world,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": 2 * W * H * 3 * 4 * (1 if banded else world),
+                    "upload": ("banded: each rank uploads H/N rows, NCCL all-gather over NVLink" if banded else "every rank uploads both images"),
                     "d2h_bytes_per_step": 2 * W * H * world, "ms_per_step": e2e_ms / args.steps},
             "e2e_u8": {"value": 1e3 / (e2e_u8_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": 2 * W * H * 3 * world,
                        "d2h_bytes_per_step": 2 * W * H * world, "ms_per_step": e2e_u8_ms / args.steps,
