@@ -34,13 +34,13 @@ struct psm_ctx {
     float* vol_alt[2] = {nullptr, nullptr}; // the other half of the ping-pong
     void* stage_in[2] = {nullptr, nullptr}; // device staging for the interleaved upload
     uint8_t* dis[2] = {nullptr, nullptr};
+    int* guide_flags = nullptr;             // [2] device flags: guide outside the integer-widening domain (see psm_cvf_stream.cuh)
     unsigned char* p2p_own = nullptr;       // own exchange block: keys [2 views][nranks][chunk] u64 + maps [2 views][H*W] u8
     unsigned char* p2p_peer[8] = {};        // every rank's exchange block as mapped here
     void* p2p_imported[8] = {};             // IPC mappings to close at destroy
     int p2p_nimported = 0, p2p_nranks = 0, p2p_rank = 0;
     float* alloc[16] = {};                  // raw cudaMalloc pointers behind the halo-offset pointers above
     int nalloc = 0;
-    bool cvf_attr_set = false;
     float* ab = nullptr;                    // naive-mode scratch [4][d_count][H][Wp], lazy
     size_t ab_slices = 0;
     cudaEvent_t ev0[kNumStages] = {}, ev1[kNumStages] = {};
@@ -110,6 +110,7 @@ int ingest(psm_ctx* c, const T* l, size_t lstep, const T* r, size_t rstep, bool 
     const T* src[2] = {l, r};
     const size_t step[2] = {lstep, rstep};
     const size_t row_bytes = (size_t)c->W * 3 * sizeof(T);
+    PSM_CUDA(c, cudaMemsetAsync(c->guide_flags, 0, 2 * sizeof(int), c->stream));
     for (int v = 0; v < 2; ++v) {
         if (!src[v] || step[v] < row_bytes) return fail(c, PSM_EINVAL, "bad image pointer/step for view %d", v);
         const T* dsrc = src[v];
@@ -123,7 +124,7 @@ int ingest(psm_ctx* c, const T* l, size_t lstep, const T* r, size_t rstep, bool 
         float* g = c->guide[v];
         dim3 blk(128), grd((c->W + 3 + 127) / 128, c->H);
         ingest_kernel<T><<<grd, blk, 0, c->stream>>>(dsrc, dstep, c->W, c->H, c->Wp, g, g + c->plane,
-                                                      g + 2 * c->plane, c->grd[v], c->gray_mode);
+                                                      g + 2 * c->plane, c->grd[v], c->gray_mode, c->guide_flags + v);
         PSM_LAUNCH_CHECK(c);
         if (int rc = pad_rows(c, g, (size_t)3 * c->H)) return rc;  // mirrored halo of the 3 guide channels
     }
@@ -138,6 +139,7 @@ int ensure_guide(psm_ctx* c)
     if (c->guide_valid) return PSM_OK;
     GuideParams P;
     P.guide[0] = c->guide[0]; P.guide[1] = c->guide[1];
+    P.guide_flags = c->guide_flags;
     P.W = c->W; P.H = c->H; P.Wp = c->Wp;
     P.nstrips = (c->W + kGuideStripOut - 1) / kGuideStripOut;
     P.nseg = (c->H + kGuideSegRows - 1) / kGuideSegRows;
@@ -199,20 +201,17 @@ int launch_cvf_stream(psm_ctx* c)
     if (c->cvf_target_rows > 0) target_rows = c->cvf_target_rows;
     plan_segments(c->H, target_rows, &P.nseg, &P.seg_rows);
     const size_t smem = (size_t)8 * 4 * nthreads * sizeof(float4) + (size_t)c->cvf_extra_smem;
-    if (!c->cvf_attr_set) {
-        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PSM_CUDA(c, cudaFuncSetAttribute(cvf_stream_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        c->cvf_attr_set = true;
-    }
+    // kernel selection: mode (exact / mixed) x tuning variant (PSM option 100)
+    //   exact: 0 = integer widening (shipped), 1 = F2F conversions everywhere (round-1 kernel, kept as the A/B baseline)
+    //   mixed: 0 = <=168 registers, 1 = <=128 registers (more resident warps when the ring allows)
+    using kern_t = void (*)(CvfParams);
+    kern_t kern = nullptr;
+    if (c->cvf_mode == PSM_CVF_MIXED) kern = c->cvf_variant == 1 ? cvf_stream_kernel<4, 1, kS2Mixed> : cvf_stream_kernel<3, 1, kS2Mixed>;
+    else kern = c->cvf_variant == 1 ? cvf_stream_kernel<3, 0, kS2Exact> : cvf_stream_kernel<3, 1, kS2Exact>;
+    PSM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    P.guide_flags = c->guide_flags;
     const unsigned grid = 2u * P.nseg * P.nstrips * P.ndgroups;
-    switch (c->cvf_variant) {  // tuning variants (PSM option 100); 0 is the shipped default
-    case 1: cvf_stream_kernel<2, 0><<<grid, nthreads, smem, c->stream>>>(P); break;
-    case 2: cvf_stream_kernel<3, 1><<<grid, nthreads, smem, c->stream>>>(P); break;
-    case 3: cvf_stream_kernel<3, 2><<<grid, nthreads, smem, c->stream>>>(P); break;
-    default: cvf_stream_kernel<3, 0><<<grid, nthreads, smem, c->stream>>>(P); break;
-    }
+    kern<<<grid, nthreads, smem, c->stream>>>(P);
     PSM_LAUNCH_CHECK(c);
     return PSM_OK;
 }
@@ -297,6 +296,8 @@ int psm_create_sharded(psm_ctx** out, int width, int height, int max_disp, int d
         PSM_CREATE_CUDA(cudaMalloc(&c->dis[v], (size_t)c->W * c->H));
         PSM_CREATE_CUDA(cudaMemsetAsync(c->dis[v], 0, (size_t)c->W * c->H, c->stream));
     }
+    PSM_CREATE_CUDA(cudaMalloc(&c->guide_flags, 2 * sizeof(int)));
+    PSM_CREATE_CUDA(cudaMemsetAsync(c->guide_flags, 0, 2 * sizeof(int), c->stream));
     for (int s = 0; s < kNumStages; ++s) {
         PSM_CREATE_CUDA(cudaEventCreate(&c->ev0[s]));
         PSM_CREATE_CUDA(cudaEventCreate(&c->ev1[s]));
@@ -322,6 +323,7 @@ int psm_destroy(psm_ctx* c)
     for (int i = 0; i < c->nalloc; ++i) cudaFree(c->alloc[i]);
     for (int v = 0; v < 2; ++v) { cudaFree(c->stage_in[v]); cudaFree(c->dis[v]); }
     cudaFree(c->ab);
+    cudaFree(c->guide_flags);
     for (int s = 0; s < kNumStages; ++s) {
         if (c->ev0[s]) cudaEventDestroy(c->ev0[s]);
         if (c->ev1[s]) cudaEventDestroy(c->ev1[s]);
@@ -339,7 +341,6 @@ int psm_set_option(psm_ctx* c, int key, int value)
     case PSM_OPT_CVF_MODE:
         if (value != PSM_CVF_EXACT && value != PSM_CVF_MIXED && value != PSM_CVF_NAIVE)
             return fail(c, PSM_EINVAL, "unknown CVF mode %d", value);
-        if (value == PSM_CVF_MIXED) return fail(c, PSM_EINVAL, "PSM_CVF_MIXED is not built in this version");
         c->cvf_mode = value;
         return PSM_OK;
     case PSM_OPT_GRAY_MODE:
@@ -358,11 +359,9 @@ int psm_set_option(psm_ctx* c, int key, int value)
     case 103:  // undocumented: threads per CTA of the streaming kernel (64 / 96 / 128)
         if (value != 0 && (value % 32 != 0 || value < 32 || value > 128)) return fail(c, PSM_EINVAL, "bad thread count");
         c->cvf_threads = value;
-        c->cvf_attr_set = false;
         return PSM_OK;
     case 102:  // undocumented: extra dynamic shared memory per CTA (bytes) to throttle occupancy in experiments
         c->cvf_extra_smem = value;
-        c->cvf_attr_set = false;
         return PSM_OK;
     case 101:  // undocumented: rows per segment of the streaming kernel (0 = automatic)
         c->cvf_target_rows = value;

@@ -5,26 +5,51 @@
 // box stages, a, b, all products and all means stay on the SM.  The reference runs ~90 Mat-sized
 // passes per slice for the same result.
 //
-// Numerics (bit-exact against the oracle):
+// Numerics
 //   * cv::boxFilter on CV_32F accumulates in double; an fp64 sum of 64 floats is exact unless the
 //     window spans > 2^23 in magnitude, so any summation order gives the same float after the one
-//     final rounding.  All eight box sums here are fp64: running column sums (+ newest row,
-//     - oldest row) and 8-wide row sums, scaled by 1/64 in fp64, rounded once to float.
-//   * every fp32 operation is a separate IEEE round-to-nearest op in the reference's order
-//     (CVF.cpp:87-163).  Multiplies of two columns share one FMUL2; adds stay scalar because
-//     ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false.
+//     final rounding.  Box sums here are fp64 running column sums (+ newest row, - oldest row) and
+//     8-wide row sums, scaled and rounded once to float.
+//   * every fp32 operation of a, b and q is a separate IEEE round-to-nearest op in the reference's
+//     order (CVF.cpp:87-163).  Multiplies of two columns share one FMUL2; adds that consume a
+//     product stay scalar because ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
+//     even with --fmad=false.
+//   * PSM_CVF_EXACT: all eight box sums in fp64 -> q bit-exact.
+//     PSM_CVF_MIXED: the four stage-1 sums in fp64 (a, b stay bit-exact), the four stage-2 sums
+//     (box of a0,a1,a2,b) in fp32 with a FIXED summation tree (below) -> q within ~3e-6 of exact,
+//     deterministic and position-independent (tests/mixed_model.py restates it on the CPU).
+//
+// f32 -> f64 without the conversion (XU) pipe.  F2F runs at 16/clk/SM on B200 and the exact filter
+// needs 24 conversions per voxel; it was the binding pipe (profiles/r1_*).  For a NON-NEGATIVE
+// finite float with bit pattern u (zero and denormals included) the 64-bit integer u * 2^29, read
+// as a double, is exactly f * 2^-896: the 8-bit exponent field lands in the low bits of the 11-bit
+// field (bias error -896), the mantissa lines up, denormals stay denormals of the same scaled
+// value, zero stays zero.  That is ONE IMAD.WIDE.U32 on the FMA pipe.  All fp64 sums are kept in
+// this 2^-896-scaled domain (a power-of-two scaling commutes with every rounding; nothing
+// underflows because the scaled values are multiples of 2^-1045 >= the fp64 denormal quantum) and
+// the scale is folded into the constant of the final multiply (2^890 instead of 2^-6).  Signed
+// values cost three integer instructions (shift the sign out, IMAD.WIDE, LOP3 the sign back in).
+// Rows whose p holds a negative, -0, inf or nan value (a warp vote per row) take a slow path that
+// converts with F2F and rescales, and from then on the warp also widens a,b with F2F, so
+// non-finite data propagates exactly like in the reference.
 //
 // Work decomposition (B200-first; nothing like the reference's per-slice Mat pipeline):
 //   warp   = one strip of 128 input columns (112 output columns) of ONE disparity slice, one row segment
 //   lane   = 4 consecutive columns -> every global access is a 128-bit load/store
-//   CTA    = 3 warps = 3 consecutive slices of the same strip and segment (guide rows hit in L1)
+//   CTA    = wpc warps = wpc consecutive slices of the same strip and segment (guide rows hit in L1)
 //   stage 1: S1[4 boxes][4 cols] fp64 running column sums of p, I0*p, I1*p, I2*p;
 //            row sums = per-lane prefix/suffix sums + 4 fp64 shuffles per box (lane+1 total, lane+2 prefixes)
 //   a,b    : CVF.cpp:92-155 with the d-independent adjugate / 1/det precomputed per pixel (K2)
-//   ring   : thread-private 8-row history of a0,a1,a2,b in shared memory (512 B per thread);
-//            the only on-chip history: stage-1 "oldest rows" are re-read from the raw volume (L1/L2)
-//   stage 2: S2[4 planes][4 cols] fp64 running column sums of a0,a1,a2,b (newest from registers,
-//            oldest from the ring); row sums as in stage 1; q = box(b) + sum_c box(a_c) * I_c
+//   ring   : thread-private 8-slot history in shared memory (512 B per thread), the only on-chip
+//            history: stage-1 "oldest rows" are re-read from the raw volume (L1/L2).
+//            EXACT: slots hold a,b rows;  MIXED: slots hold PAIR rows  pair(t) = ab(t-1) + ab(t)
+//   stage 2 EXACT: S2[4 planes][4 cols] fp64 running column sums of a0,a1,a2,b (newest from
+//            registers, oldest from the ring); row sums as in stage 1
+//   stage 2 MIXED: V(y) = (P(y-3) + P(y-1)) + (P(y+1) + P(y+3)), P(s) = X[r(s-1)] + X[r(s)] with
+//            reflected rows, i.e. the tree ((x0+x1)+(x2+x3))+((x4+x5)+(x6+x7)) over window rows
+//            y-4..y+3; row sums by the same prefix/suffix scheme in fp32 over ALIGNED 4-column
+//            groups (strip origins are multiples of 4, so the tree depends on x only)
+//   q = box(b) + sum_c box(a_c) * I_c   (CVF.cpp:157-163)
 //
 // Column bookkeeping of strip s (X0 = first output column, 112*s; the last strip is shifted left
 // to end at the image edge), lane l:
@@ -36,21 +61,29 @@
 // is asymmetric) -- so border strips overwrite those entries by lane shuffles.
 // Rows: the top of the image uses weights 1,2,2,2,1 for the first window, the bottom feeds three
 // virtual rows from the ring; input rows reflect by index.  These special cases live in
-// generic_step; the bulk of the rows run steady_step, which has no conditionals at all.
+// generic_step; the bulk of the rows run the steady step, which has no data-dependent control
+// flow except the warp-uniform fast/slow widening choice.
 #pragma once
+#include <type_traits>
+
 #include "psm_kernels.cuh"
 
 namespace psm {
 
 constexpr int kStripOut = 112;  // output columns per warp
 constexpr int kStripIn = 128;   // input columns per warp
-constexpr int kCvfThreads = 96;       // shipped CTA size: 3 slice-warps, 48 KB ring, 4 CTAs/SM (measured best of 32/64/96/128)
+constexpr int kCvfThreads = 96;       // default CTA size: 3 slice-warps, 48 KB ring, 4 CTAs/SM
 constexpr int kCvfMaxThreads = 128;   // upper bound the register allocation is sized for
+
+// stage-2 modes (template parameter S2M)
+constexpr int kS2Exact = 0;  // fp64 running sums
+constexpr int kS2Mixed = 1;  // fp32 pair tree (PSM_CVF_MIXED)
 
 struct CvfParams {
     const float* vol_in[2];   // raw volumes  [Dloc][H][Wp]   (pointer to row 0, column 0)
     float* vol_out[2];        // filtered volumes
     const float* guide[2];    // guide planes [kGuidePlanes][H][Wp]
+    const int* guide_flags;   // [2] per view: != 0 when the guide holds negative / non-finite values
     int W, H, Wp, Dloc;
     int nstrips, nseg, seg_rows, ndgroups;
     int remap_sms, remap_ctas;  // SM count and resident CTAs per SM for the block->work remap (0: identity)
@@ -68,37 +101,73 @@ __device__ __forceinline__ f2x2 sub2(const f2x2& a, const f2x2& b)
 {
     return {make_float2(fsub(a.lo.x, b.lo.x), fsub(a.lo.y, b.lo.y)), make_float2(fsub(a.hi.x, b.hi.x), fsub(a.hi.y, b.hi.y))};
 }
+// packed add (FADD2): only for operands that are NOT products (see the contraction note above)
+__device__ __forceinline__ f2x2 addp(const f2x2& a, const f2x2& b) { return {__fadd2_rn(a.lo, b.lo), __fadd2_rn(a.hi, b.hi)}; }
 __device__ __forceinline__ float get(const f2x2& v, int j) { return j == 0 ? v.lo.x : (j == 1 ? v.lo.y : (j == 2 ? v.hi.x : v.hi.y)); }
 
-// f32 -> f64 without the conversion pipe: for a positive normal float the double is
-// {hi = (u >> 3) + 0x38000000, lo = u << 29}; everything else (zero, denormal, negative, inf, nan)
-// takes the F2F instruction under a predicate that is almost never set.  Stage-1 inputs (p and
-// I*p) are non-negative, so on real data the XU pipe is spared these conversions.
-__device__ __forceinline__ double widen_pos(float f)
+// ---- widening into the 2^-896-scaled fp64 domain --------------------------------------------
+constexpr double kScaleDown = 0x1p-896;   // what the integer widening multiplies by
+constexpr double kMeanScaled = 0x1p890;   // 2^896 / 64
+constexpr double kMeanPlain = 0x1p-6;     // 1 / 64
+
+// non-negative finite float (zero / denormal included): one IMAD.WIDE.U32
+__device__ __forceinline__ double widen_nn(float f)
+{
+    unsigned long long r;
+    asm("mul.wide.u32 %0, %1, 0x20000000;" : "=l"(r) : "r"(__float_as_uint(f)));
+    return __longlong_as_double((long long)r);
+}
+// any finite float: shift the sign out, widen, put the sign back
+__device__ __forceinline__ double widen_sg(float f)
 {
     const unsigned u = __float_as_uint(f);
-    double d = __hiloint2double((int)((u >> 3) + 0x38000000u), (int)(u << 29));
-    if (u - 0x00800000u >= 0x7f000000u) d = (double)f;
-    return d;
+    unsigned long long r;
+    asm("mul.wide.u32 %0, %1, 0x10000000;" : "=l"(r) : "r"(u + u));
+    const unsigned hi = (unsigned)(r >> 32) | (u & 0x80000000u);
+    return __hiloint2double((int)hi, (int)(unsigned)r);
 }
-
-__device__ __forceinline__ float mean64(double s) { return (float)__dmul_rn(s, 1.0 / 64.0); }
+// anything (slow path): conversion pipe + exact rescale
+__device__ __forceinline__ double widen_any(float f) { return __dmul_rn((double)f, kScaleDown); }
 
 __device__ __forceinline__ float4 ldg4(const char* __restrict__ p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ unsigned umax4(const float4& v)
+{
+    return max(max(__float_as_uint(v.x), __float_as_uint(v.y)), max(__float_as_uint(v.z), __float_as_uint(v.w)));
+}
 
-// MINB: resident CTAs per SM the register allocation is sized for (3 -> <=168 regs, 2 -> <=255);
-// IW: integer widening (widen_pos) of the stage-1 inputs: 0 none, 1 oldest rows, 2 newest + oldest rows.
-template <int MINB, int IW>
+// fp32 8-wide window sums from the 4 column sums a lane owns (MIXED stage 2), same tree as hsum8
+__device__ __forceinline__ f2x2 hsum8f(const f2x2& c)
+{
+    const float c0 = c.lo.x, c1 = c.lo.y, c2 = c.hi.x, c3 = c.hi.y;
+    const float P2 = __fadd_rn(c0, c1), P3 = __fadd_rn(P2, c2), Tt = __fadd_rn(P3, c3);
+    const float S2 = __fadd_rn(c2, c3), S3 = __fadd_rn(c1, S2);
+    const float Tn = __shfl_down_sync(0xffffffffu, Tt, 1);
+    const float Q1 = __shfl_down_sync(0xffffffffu, c0, 2);
+    const float Q2 = __shfl_down_sync(0xffffffffu, P2, 2);
+    const float Q3 = __shfl_down_sync(0xffffffffu, P3, 2);
+    f2x2 h;
+    h.lo.x = __fadd_rn(Tt, Tn);
+    h.lo.y = __fadd_rn(__fadd_rn(S3, Tn), Q1);
+    h.hi.x = __fadd_rn(__fadd_rn(S2, Tn), Q2);
+    h.hi.y = __fadd_rn(__fadd_rn(c3, Tn), Q3);
+    return h;
+}
+
+// MINB: resident CTAs per SM the register allocation is sized for (3 -> <=168 regs, 4 -> <=128);
+// IW  : 1 = integer widening into the scaled domain (stage 1, and stage 2 when exact), 0 = F2F everywhere
+// S2M : kS2Exact / kS2Mixed
+template <int MINB, int IW, int S2M>
 __global__ void __launch_bounds__(kCvfMaxThreads, MINB)
 cvf_stream_kernel(const CvfParams P)
 {
     extern __shared__ float4 ring[];  // [8 slots][4 planes][blockDim.x threads]
-    constexpr bool IWN = IW >= 2, IWO = IW >= 1;
+    constexpr bool MIXED = (S2M == kS2Mixed);
+    constexpr double kMean1 = IW ? kMeanScaled : kMeanPlain;   // stage-1 mean scale
+    constexpr double kMean2 = IW ? kMeanScaled : kMeanPlain;   // stage-2 (exact) mean scale
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int nthr = blockDim.x;            // kCvfThreads in the shipped configuration (option 103 varies it)
+    const int nthr = blockDim.x;
     const int wpc = nthr >> 5;
 
     // Block -> work mapping.  Hardware hands consecutive blockIdx to consecutive SMs, so the CTAs that
@@ -114,9 +183,8 @@ cvf_stream_kernel(const CvfParams P)
     const int strip = b % P.nstrips;   b /= P.nstrips;
     const int seg = b % P.nseg;
     const int view = b / P.nseg;
-    const bool slice_ok = dgroup * wpc + warp < P.Dloc;
-    const int dlc = slice_ok ? dgroup * wpc + warp : P.Dloc - 1;  // surplus warps redo the last slice, stores masked
-    if (!slice_ok) return;  // warps never synchronise with each other
+    const int dlc = dgroup * wpc + warp;
+    if (dlc >= P.Dloc) return;  // warps never synchronise with each other
 
     const int W = P.W, H = P.H;
     const unsigned Wp = (unsigned)P.Wp;
@@ -131,7 +199,12 @@ cvf_stream_kernel(const CvfParams P)
     const char* __restrict__ vin = reinterpret_cast<const char*>(P.vol_in[view] + (size_t)dlc * plane + cin);
     char* __restrict__ vout = reinterpret_cast<char*>(P.vol_out[view] + (size_t)dlc * plane + cin + 8);
     const size_t planeB = (size_t)plane * 4, rowB = (size_t)Wp * 4;
-    const bool store_ok = slice_ok && lane <= 27 && cin + 8 < W && cin + 8 >= out_lo;
+    const bool store_ok = lane <= 27 && cin + 8 < W && cin + 8 >= out_lo;
+
+    // a guide with negative / non-finite values (outside the [0,1] image contract) disables the
+    // integer widening for the whole launch of this view; `slow` also turns sticky once a row of p
+    // needed the slow path, so that non-finite a,b are widened by F2F as well
+    bool slow = IW ? (__ldg(P.guide_flags + view) != 0) : true;
 
     // ---- x-reflection plan for a,b (strips whose a,b columns X0-4 .. X0+115 leave the image) ----
     const bool fix_left = X0 == 0;
@@ -158,11 +231,17 @@ cvf_stream_kernel(const CvfParams P)
     const int Tlast = bottom ? H - 1 : Y1 + 2;    // last real a,b row
     const int Tend = bottom ? H + 2 : Tlast;      // last step (three virtual rows below the image)
 
-    double S1[4][4], S2[4][4];
+    double S1[4][4];
+    double S2[MIXED ? 1 : 4][4];
+    f2x2 prev[MIXED ? 4 : 1];     // MIXED: a,b row t-1
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { S1[q][j] = 0.0; S2[q][j] = 0.0; }
+        for (int j = 0; j < 4; ++j) { S1[q][j] = 0.0; S2[MIXED ? 0 : q][j] = 0.0; }
+    if (MIXED) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) prev[q] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    }
 
     struct RowIn { float4 p, i0, i1, i2; };
     auto load_at = [&](size_t ro) {  // ro: byte offset of the row
@@ -174,42 +253,67 @@ cvf_stream_kernel(const CvfParams P)
         return x;
     };
     auto load_row = [&](int r) { return load_at((size_t)reflect101(r, H) * rowB); };
-    auto add_row = [&](const RowIn& x) {
+    // warp-uniform: true when some lane's p holds a negative (incl. -0), inf or nan value
+    auto needs_slow = [&](const float4& pa, const float4& pb) {
+        return __any_sync(0xffffffffu, max(umax4(pa), umax4(pb)) >= 0x7f800000u) != 0;
+    };
+    // S1 += / -= one input row.  WID: 0 F2F unscaled, 1 integer non-negative (scaled), 2 F2F scaled
+    auto acc_row = [&](const RowIn& x, auto wid_tag, auto sub_tag) {
+        constexpr int WID = decltype(wid_tag)::value;
+        constexpr bool SUB = decltype(sub_tag)::value;
         const f2x2 p = from4(x.p);
         const f2x2 m0 = mul2(from4(x.i0), p), m1 = mul2(from4(x.i1), p), m2 = mul2(from4(x.i2), p);  // CVF.cpp:87
+        auto w = [](float f) { return WID == 0 ? (double)f : (WID == 1 ? widen_nn(f) : widen_any(f)); };
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            S1[0][j] = __dadd_rn(S1[0][j], IWN ? widen_pos(get(p, j)) : (double)get(p, j));
-            S1[1][j] = __dadd_rn(S1[1][j], IWN ? widen_pos(get(m0, j)) : (double)get(m0, j));
-            S1[2][j] = __dadd_rn(S1[2][j], IWN ? widen_pos(get(m1, j)) : (double)get(m1, j));
-            S1[3][j] = __dadd_rn(S1[3][j], IWN ? widen_pos(get(m2, j)) : (double)get(m2, j));
+            if (SUB) {
+                S1[0][j] = __dsub_rn(S1[0][j], w(get(p, j)));
+                S1[1][j] = __dsub_rn(S1[1][j], w(get(m0, j)));
+                S1[2][j] = __dsub_rn(S1[2][j], w(get(m1, j)));
+                S1[3][j] = __dsub_rn(S1[3][j], w(get(m2, j)));
+            } else {
+                S1[0][j] = __dadd_rn(S1[0][j], w(get(p, j)));
+                S1[1][j] = __dadd_rn(S1[1][j], w(get(m0, j)));
+                S1[2][j] = __dadd_rn(S1[2][j], w(get(m1, j)));
+                S1[3][j] = __dadd_rn(S1[3][j], w(get(m2, j)));
+            }
         }
     };
-    auto sub_row = [&](const RowIn& x) {
-        const f2x2 p = from4(x.p);
-        const f2x2 m0 = mul2(from4(x.i0), p), m1 = mul2(from4(x.i1), p), m2 = mul2(from4(x.i2), p);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            S1[0][j] = __dsub_rn(S1[0][j], IWO ? widen_pos(get(p, j)) : (double)get(p, j));
-            S1[1][j] = __dsub_rn(S1[1][j], IWO ? widen_pos(get(m0, j)) : (double)get(m0, j));
-            S1[2][j] = __dsub_rn(S1[2][j], IWO ? widen_pos(get(m1, j)) : (double)get(m1, j));
-            S1[3][j] = __dsub_rn(S1[3][j], IWO ? widen_pos(get(m2, j)) : (double)get(m2, j));
-        }
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    using Tadd = std::false_type;
+    using Tsub = std::true_type;
+    auto add_row = [&](const RowIn& x, bool slow_row) {
+        if (!IW) acc_row(x, I0{}, Tadd{});
+        else if (slow_row) acc_row(x, I2{}, Tadd{});
+        else acc_row(x, I1{}, Tadd{});
+    };
+    auto sub_row = [&](const RowIn& x, bool slow_row) {
+        if (!IW) acc_row(x, I0{}, Tsub{});
+        else if (slow_row) acc_row(x, I2{}, Tsub{});
+        else acc_row(x, I1{}, Tsub{});
     };
     auto load_guide = [&](size_t ro, float4 (&g4)[10]) {
 #pragma unroll
         for (int q = 0; q < 10; ++q) g4[q] = ldg4(Ga + ((size_t)(kGuideMean + q) * planeB + ro));
     };
+    auto mean4 = [](const double (&h)[4], double scale) {
+        f2x2 m;
+        m.lo = make_float2((float)__dmul_rn(h[0], scale), (float)__dmul_rn(h[1], scale));
+        m.hi = make_float2((float)__dmul_rn(h[2], scale), (float)__dmul_rn(h[3], scale));
+        return m;
+    };
 
     // stage-1 row sums -> means -> cov -> a,b (CVF.cpp:81-155), then the x-reflection of a,b
     auto coeffs = [&](const float4 (&g4)[10], f2x2 (&av)[4]) {
-        double h[4][4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) hsum8(S1[q], h[q]);
         f2x2 m[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            m[q] = {make_float2(mean64(h[q][0]), mean64(h[q][1])), make_float2(mean64(h[q][2]), mean64(h[q][3]))};
+        for (int q = 0; q < 4; ++q) {
+            double h[4];
+            hsum8(S1[q], h);
+            m[q] = mean4(h, kMean1);
+        }
         const f2x2 mI0 = from4(g4[0]), mI1 = from4(g4[1]), mI2 = from4(g4[2]);
         const f2x2 M00 = from4(g4[3]), M01 = from4(g4[4]), M02 = from4(g4[5]);
         const f2x2 M11 = from4(g4[6]), M12 = from4(g4[7]), M22 = from4(g4[8]);
@@ -247,21 +351,41 @@ cvf_stream_kernel(const CvfParams P)
         }
     };
 
-    // stage-2 row sums -> q for one output row; i* are the guide channels at the output columns
-    auto emit = [&](size_t ro, const float4& i0, const float4& i1, const float4& i2) {
-        double h2[4][4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) hsum8(S2[q], h2[q]);
-        f2x2 mb[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            mb[q] = {make_float2(mean64(h2[q][0]), mean64(h2[q][1])), make_float2(mean64(h2[q][2]), mean64(h2[q][3]))};
-        // q = box(b) + box(a0)*I0 + box(a1)*I1 + box(a2)*I2, accumulated in that order (CVF.cpp:157-163)
+    // q = box(b) + box(a0)*I0 + box(a1)*I1 + box(a2)*I2, accumulated in that order (CVF.cpp:157-163)
+    auto combine = [&](size_t ro, const f2x2 (&mb)[4], const float4& i0, const float4& i1, const float4& i2) {
         f2x2 qv = add2(mb[3], mul2(mb[0], from4(i0)));
         qv = add2(qv, mul2(mb[1], from4(i1)));
         qv = add2(qv, mul2(mb[2], from4(i2)));
         if (store_ok) *reinterpret_cast<float4*>(vout + ro) = to4(qv);
     };
+    // EXACT: stage-2 row sums of S2 -> q for one output row
+    auto emit = [&](size_t ro, const float4& i0, const float4& i1, const float4& i2) {
+        f2x2 mb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double h2[4];
+            hsum8(S2[MIXED ? 0 : q], h2);
+            mb[q] = mean4(h2, kMean2);
+        }
+        combine(ro, mb, i0, i1, i2);
+    };
+    // MIXED: the four pair rows of one window -> q for one output row
+    auto emit_pairs = [&](size_t ro, const f2x2 (&pa)[4], const f2x2 (&pb)[4], const f2x2 (&pc)[4], const f2x2 (&pd)[4],
+                          const float4& i0, const float4& i1, const float4& i2) {
+        f2x2 mb[4];
+        const f2x2 k64 = {make_float2(1.f / 64.f, 1.f / 64.f), make_float2(1.f / 64.f, 1.f / 64.f)};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const f2x2 v = addp(addp(pa[q], pb[q]), addp(pc[q], pd[q]));  // (P(y-3)+P(y-1)) + (P(y+1)+P(y+3))
+            mb[q] = mul2(hsum8f(v), k64);
+        }
+        combine(ro, mb, i0, i1, i2);
+    };
+    // widening of a,b values for the exact stage 2
+    auto w2 = [&](float f, bool slow_now) { return !IW ? (double)f : (slow_now ? widen_any(f) : widen_sg(f)); };
+
+    // MIXED: pair-row index with the row reflection folded in: P(s) = pair(refl_p(s))
+    auto refl_p = [&](int s) { return s <= 0 ? 1 - s : (s >= H ? 2 * H - 1 - s : s); };
 
     // ---- generic step: any row, every special case (top weights, warm-up, reflection, virtual rows)
     auto generic_step = [&](int t) {
@@ -272,39 +396,65 @@ cvf_stream_kernel(const CvfParams P)
             const RowIn xo = load_row(t - 4);
             float4 g4[10];
             load_guide((size_t)t * rowB, g4);
-            add_row(xn);
+            const bool slow_row = slow || (IW && needs_slow(xn.p, xo.p));
+            slow = slow_row;   // sticky
+            add_row(xn, slow_row);
             coeffs(g4, av);
-            sub_row(xo);
-        } else {  // virtual a,b row below the image == reflected row, still in the ring
-            const int slot = reflect101(t, H) & 7;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) av[q] = from4(ring[(slot * 4 + q) * nthr + tid]);
+            sub_row(xo, slow_row);
         }
         const int age = t - T0;
         const bool warm = top ? (t <= 4) : (age < 8);
-        const double wnew = (top && t >= 1 && t <= 3) ? 2.0 : 1.0;      // rows 1..3 appear twice in row 0's window
-        const int oslot = (top && t < 8) ? ((8 - t) & 7) : (t & 7);      // slot of a,b row reflect(t-8)
-        const int nslot = t & 7;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float4 old4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!warm) old4 = ring[(oslot * 4 + q) * nthr + tid];
-            if (real_row) ring[(nslot * 4 + q) * nthr + tid] = to4(av[q]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                double s = __fma_rn(wnew, (double)get(av[q], j), S2[q][j]);  // exact: wnew is 1 or 2
-                if (!warm) s = __dsub_rn(s, (double)comp(old4, j));
-                S2[q][j] = s;
-            }
-        }
         const bool first_out = top ? (t == 4) : (age == 7);
+        if (!MIXED) {
+            if (!real_row) {  // virtual a,b row below the image == reflected row, still in the ring
+                const int slot = reflect101(t, H) & 7;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) av[q] = from4(ring[(slot * 4 + q) * nthr + tid]);
+            }
+            const double wnew = (top && t >= 1 && t <= 3) ? 2.0 : 1.0;      // rows 1..3 appear twice in row 0's window
+            const int oslot = (top && t < 8) ? ((8 - t) & 7) : (t & 7);      // slot of a,b row reflect(t-8)
+            const int nslot = t & 7;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 old4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!warm) old4 = ring[(oslot * 4 + q) * nthr + tid];
+                if (real_row) ring[(nslot * 4 + q) * nthr + tid] = to4(av[q]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double s = __fma_rn(wnew, w2(get(av[q], j), slow), S2[MIXED ? 0 : q][j]);  // exact: wnew is 1 or 2
+                    if (!warm) s = __dsub_rn(s, w2(comp(old4, j), slow));
+                    S2[MIXED ? 0 : q][j] = s;
+                }
+            }
+        } else if (real_row) {
+            if (t > T0) {  // pair(t) = ab(t-1) + ab(t); the first row of a segment has no predecessor
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ring[((t & 7) * 4 + q) * nthr + tid] = to4(add2(av[q], prev[q]));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) prev[q] = av[q];
+        }
         if (warm && !first_out) return;
         const int nrows = (top && t == 4) ? 2 : 1;  // output rows 0 and 1 share one reflected window
         for (int e = 0; e < nrows; ++e) {
             const int y = (top && t == 4) ? e : t - 3;
             if (y < Y0 || y >= Y1) continue;
             const size_t ro = (size_t)y * rowB;
-            emit(ro, ldg4(Go + ro), ldg4(Go + (planeB + ro)), ldg4(Go + (2 * planeB + ro)));
+            const float4 o0 = ldg4(Go + ro), o1 = ldg4(Go + (planeB + ro)), o2 = ldg4(Go + (2 * planeB + ro));
+            if (!MIXED) {
+                emit(ro, o0, o1, o2);
+            } else {
+                f2x2 pa[4], pb[4], pc[4], pd[4];
+                const int sa = refl_p(y - 3) & 7, sb = refl_p(y - 1) & 7, sc = refl_p(y + 1) & 7, sd = refl_p(y + 3) & 7;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    pa[q] = from4(ring[(sa * 4 + q) * nthr + tid]);
+                    pb[q] = from4(ring[(sb * 4 + q) * nthr + tid]);
+                    pc[q] = from4(ring[(sc * 4 + q) * nthr + tid]);
+                    pd[q] = from4(ring[(sd * 4 + q) * nthr + tid]);
+                }
+                emit_pairs(ro, pa, pb, pc, pd, o0, o1, o2);
+            }
         }
     };
 
@@ -314,7 +464,12 @@ cvf_stream_kernel(const CvfParams P)
     const int Ts0 = top ? 8 : T0 + 8;
     const int Ts1 = min(Tlast, H - 5);
 
-    for (int r = T0 - 4; r <= T0 + 2; ++r) add_row(load_row(r));
+    for (int r = T0 - 4; r <= T0 + 2; ++r) {
+        const RowIn x = load_row(r);
+        const bool slow_row = slow || (IW && needs_slow(x.p, x.p));
+        slow = slow_row;
+        add_row(x, slow_row);
+    }
     int t = T0;
     for (; t <= Tend && t < Ts0; ++t) generic_step(t);
 
@@ -325,39 +480,64 @@ cvf_stream_kernel(const CvfParams P)
         size_t ro_y = (size_t)(t - 3) * rowB;  // output row        t-3
         RowIn xn = load_at(ro_n);   // newest row of the next stage-1 step (loaded one step ahead)
         RowIn xo = load_at(ro_o);   // oldest row of the next stage-1 step (loaded one step ahead)
-        // stage 1 of a,b row ro_t: S1 += newest, row sums -> a,b, S1 -= oldest; refills xn / xo
-        auto stage1 = [&](f2x2 (&av)[4]) {
-            float4 g4[10];
-            load_guide(ro_t, g4);
-            add_row(xn);
-            ro_n += rowB;
-            xn = load_at(ro_n);     // into the registers add_row just released
-            coeffs(g4, av);
-            sub_row(xo);
-            ro_o += rowB;
-            xo = load_at(ro_o);
-            ro_t += rowB;
-        };
-        // stage 2 of a,b row tt (output row tt-3 at byte offset ro_y): ring exchange, S2 update, q
-        auto stage2 = [&](int tt, const f2x2 (&av)[4], const float4& o0, const float4& o1, const float4& o2) {
-            float4* rp = ring + ((tt & 7) * 4) * nthr + tid;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 old4 = rp[q * nthr];
-                rp[q * nthr] = to4(av[q]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    S2[q][j] = __dsub_rn(__dadd_rn(S2[q][j], (double)get(av[q], j)), (double)comp(old4, j));
-            }
-            emit(ro_y, o0, o1, o2);
-            ro_y += rowB;
-        };
-        for (; t <= Ts1; ++t) {
+        // One steady step.  SLOW (compile time) selects the F2F widening for rows outside the integer
+        // domain; the fast loop below leaves for the slow loop the first time a vote says so and never
+        // comes back (sticky), so the fast loop is straight-line code.
+        auto steady = [&](auto slow_tag) {
+            constexpr bool SLOW = decltype(slow_tag)::value;
             const float4 o0 = ldg4(Go + ro_y), o1 = ldg4(Go + (planeB + ro_y)), o2 = ldg4(Go + (2 * planeB + ro_y));
             f2x2 av[4];
-            stage1(av);
-            stage2(t, av, o0, o1, o2);
+            {   // stage 1 of a,b row ro_t: S1 += newest, row sums -> a,b, S1 -= oldest; refills xn / xo
+                float4 g4[10];
+                load_guide(ro_t, g4);
+                add_row(xn, SLOW);
+                ro_n += rowB;
+                xn = load_at(ro_n);     // into the registers add_row just released
+                coeffs(g4, av);
+                sub_row(xo, SLOW);
+                ro_o += rowB;
+                xo = load_at(ro_o);
+                ro_t += rowB;
+            }
+            if (!MIXED) {
+                // stage 2 (exact) of a,b row t (output row t-3): ring exchange, S2 update, q
+                float4* rp = ring + ((t & 7) * 4) * nthr + tid;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 old4 = rp[q * nthr];
+                    rp[q * nthr] = to4(av[q]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        S2[MIXED ? 0 : q][j] = __dsub_rn(__dadd_rn(S2[MIXED ? 0 : q][j], w2(get(av[q], j), SLOW)), w2(comp(old4, j), SLOW));
+                }
+                emit(ro_y, o0, o1, o2);
+            } else {
+                // stage 2 (mixed): pair(t) into the ring, window = (pair(t-6)+pair(t-4)) + (pair(t-2)+pair(t))
+                f2x2 pa[4], pb[4], pc[4], pd[4];
+                const float4* r6 = ring + (((t - 6) & 7) * 4) * nthr + tid;
+                const float4* r4 = ring + (((t - 4) & 7) * 4) * nthr + tid;
+                const float4* r2 = ring + (((t - 2) & 7) * 4) * nthr + tid;
+                float4* r0 = ring + ((t & 7) * 4) * nthr + tid;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    pa[q] = from4(r6[q * nthr]);
+                    pb[q] = from4(r4[q * nthr]);
+                    pc[q] = from4(r2[q * nthr]);
+                    pd[q] = add2(av[q], prev[q]);
+                    r0[q * nthr] = to4(pd[q]);
+                    prev[q] = av[q];
+                }
+                emit_pairs(ro_y, pa, pb, pc, pd, o0, o1, o2);
+            }
+            ro_y += rowB;
+        };
+        if (IW) {
+            for (; t <= Ts1 && !slow; ++t) {
+                if (needs_slow(xn.p, xo.p)) { slow = true; break; }
+                steady(std::false_type{});
+            }
         }
+        for (; t <= Ts1; ++t) steady(std::true_type{});
     }
     for (; t <= Tend; ++t) generic_step(t);
 }

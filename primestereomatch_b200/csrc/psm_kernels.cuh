@@ -60,7 +60,7 @@ __device__ __forceinline__ float gray_at(const T* __restrict__ row, int x, int g
 template <typename T>
 __global__ void ingest_kernel(const T* __restrict__ src, size_t step_bytes, int W, int H, int Wp,
                               float* __restrict__ I0, float* __restrict__ I1, float* __restrict__ I2,
-                              float* __restrict__ grd, int gray_mode)
+                              float* __restrict__ grd, int gray_mode, int* __restrict__ guide_flag)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
@@ -68,9 +68,13 @@ __global__ void ingest_kernel(const T* __restrict__ src, size_t step_bytes, int 
     const size_t o = (size_t)y * Wp + x;
     if (x >= W) { I0[o] = 0.f; I1[o] = 0.f; I2[o] = 0.f; grd[o] = 0.f; return; }
     const T* row = reinterpret_cast<const T*>(reinterpret_cast<const char*>(src) + (size_t)y * step_bytes);
-    I0[o] = to_f32(row[3 * x]);
-    I1[o] = to_f32(row[3 * x + 1]);
-    I2[o] = to_f32(row[3 * x + 2]);
+    const float v0 = to_f32(row[3 * x]), v1 = to_f32(row[3 * x + 1]), v2 = to_f32(row[3 * x + 2]);
+    I0[o] = v0;
+    I1[o] = v1;
+    I2[o] = v2;
+    // the CVF kernel's integer widening assumes I >= +0 and finite (images are in [0,1] by contract,
+    // DispEst data contract SURVEY 8b); anything else raises the per-view flag and selects its slow path
+    if (max(max(__float_as_uint(v0), __float_as_uint(v1)), __float_as_uint(v2)) >= 0x7f800000u) atomicOr(guide_flag, 1);
     const float gr = gray_at(row, reflect101(x + 1, W), gray_mode);
     const float gl = gray_at(row, reflect101(x - 1, W), gray_mode);
     grd[o] = fsub(gr, gl);
@@ -278,6 +282,7 @@ constexpr int kGuideStripOut = 120;
 
 struct GuideParams {
     float* guide[2];
+    int* guide_flags;   // [2]: bit 1 raised when a mean / adjugate / 1/det value is not finite
     int W, H, Wp, nstrips, nseg;
 };
 
@@ -348,9 +353,16 @@ __global__ void __launch_bounds__(128) guide_kernel(const GuideParams P)
         }
         if (out_ok) {
             const size_t oo = (size_t)y * Wp + co;
+            unsigned worst = 0;
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
+            for (int k = 0; k < 16; ++k) {
                 *reinterpret_cast<float4*>(G + (size_t)(kGuideMean + k) * plane + oo) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+                if (k < 10) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) worst = max(worst, __float_as_uint(o[k][j]) & 0x7fffffffu);
+                }
+            }
+            if (worst >= 0x7f800000u) atomicOr(P.guide_flags + view, 2);
         }
     }
 }

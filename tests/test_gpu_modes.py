@@ -1,0 +1,128 @@
+"""GPU tests of the CVF kernel's modes and paths (all through the C-ABI):
+  * PSM_CVF_EXACT with integer widening (shipped) and with F2F conversions (round-1 kernel) -- both bit-exact;
+  * inputs outside the integer-widening domain (negative / -0 costs, negative guide values) -- bit-exact through
+    the per-row slow path and the guide flag;
+  * PSM_CVF_MIXED -- bit-exact against its CPU model (tests/mixed_model.py), within tolerance of the exact path;
+  * BASELINE config C3 (1280x720x64) at full size against the oracle."""
+import numpy as np
+import pytest
+
+import mixed_model as MM
+from primestereomatch_b200 import DispEst, capi, synth
+from test_gpu_parity import assert_same, run_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_exact_variants_bit_exact(variant, scenes, oracle_scene_results):
+    _, _, l, r = scenes["Teddy"]
+    ref = oracle_scene_results["Teddy"]
+    g = run_gpu(l, r, 64, variant=variant)
+    assert_same(g["lf"], ref["lf"], f"left filtered, variant {variant}")
+    assert_same(g["rf"], ref["rf"], f"right filtered, variant {variant}")
+    assert_same(g["ld"], ref["ld"], "lDisMap")
+    assert_same(g["rd"], ref["rd"], "rDisMap")
+
+
+def test_costs_outside_the_integer_domain(oracle):
+    """Negative and -0 costs in a few rows (the rest of the volume is ordinary): the affected warps leave
+    the integer-widening loop for the F2F loop mid-segment; everything stays bit-exact."""
+    rng = np.random.default_rng(17)
+    H, W, D = 300, 260, 5
+    l = rng.random((H, W, 3), dtype=np.float32)
+    vol = np.abs(rng.normal(0, 1, (D, H, W))).astype(np.float32)
+    vol[1, 140:143, 30:60] *= -1.0        # negative costs in the steady part of a segment
+    vol[2, 5, :] = -0.0                   # -0 in the warm-up rows
+    vol[3, 290:, 200:] *= -1.0            # negative costs at the bottom
+    vol[4, :, :] = 0.0                    # exact zeros everywhere stay on the fast path
+    rgb, mean, var = oracle.cvf_preprocess(l)
+    want = np.stack([oracle.guided_filter(rgb, mean, var, vol[d]) for d in range(D)])
+    with DispEst(l, l, D) as de:
+        de.CostConst_GPU()
+        for d in range(D):
+            de.write_cost_slice(0, d, vol[d]); de.write_cost_slice(1, d, vol[d])
+        de.CostFilter_GPU()
+        assert_same(de.read_cost_volume(0), want, "filtered volume with negative / -0 costs")
+        assert_same(de.read_cost_volume(1), want, "right view")
+
+
+def test_guide_outside_the_integer_domain(oracle):
+    """Images are in [0,1] by contract; a negative channel value raises the guide flag and the whole
+    launch of that view converts with F2F -- still the oracle's result."""
+    rng = np.random.default_rng(23)
+    H, W, D = 64, 150, 6
+    l = rng.random((H, W, 3), dtype=np.float32)
+    r = np.roll(l, -2, axis=1).copy()
+    l[10, 20, 1] = -0.25
+    ref = oracle.pipeline(l, r, D, keep_volumes=True)
+    g = run_gpu(l, r, D)
+    assert_same(g["lf"], ref["lVol"], "left filtered (negative guide value)")
+    assert_same(g["rf"], ref["rVol"], "right filtered")
+    assert_same(g["ld"], ref["lDis"], "lDisMap")
+
+
+@pytest.mark.parametrize("scene", ["Cones", "Teddy"])
+def test_mixed_mode_matches_its_model_and_tolerance(scene, scenes, oracle, oracle_scene_results):
+    _, _, l, r = scenes[scene]
+    ref = oracle_scene_results[scene]
+    g = run_gpu(l, r, 64, mode=capi.PSM_CVF_MIXED)
+    assert_same(g["lraw"], ref["lraw"], "raw volume is mode-independent")
+    for view, img, raw, key in ((0, l, ref["lraw"], "lf"), (1, r, ref["rraw"], "rf")):
+        want = MM.cost_filter_mixed(oracle, img, raw)
+        assert_same(g[key], want, f"MIXED filtered volume vs CPU model, view {view}")
+        assert np.max(np.abs(g[key] - ref[key])) <= 1e-5
+    for got, exact in ((g["ld"], ref["ld"]), (g["rd"], ref["rd"])):
+        diff = np.abs(got.astype(np.int16) - exact.astype(np.int16))
+        assert int((diff > 1).sum()) == 0          # north-star: +-1 disparity level
+        assert int((diff > 0).sum()) == 0          # in fact identical maps on both scenes
+
+
+@pytest.mark.parametrize("W,H,D", [(16, 16, 4), (17, 23, 5), (113, 40, 8), (130, 50, 9), (225, 33, 16),
+                                   (451, 64, 12), (64, 300, 6), (340, 17, 3)])
+def test_mixed_mode_ragged_sizes(W, H, D, oracle):
+    rng = np.random.default_rng(W * 1000 + H)
+    l = rng.random((H, W, 3), dtype=np.float32)
+    r = np.clip(np.roll(l, -3, axis=1) + rng.normal(0, 0.02, (H, W, 3)), 0, 1).astype(np.float32)
+    _, _, lraw, rraw = oracle.cost_const(l, r, D)
+    g = run_gpu(l, r, D, mode=capi.PSM_CVF_MIXED)
+    assert_same(g["lf"], MM.cost_filter_mixed(oracle, l, lraw), f"MIXED left {W}x{H}x{D}")
+    assert_same(g["rf"], MM.cost_filter_mixed(oracle, r, rraw), f"MIXED right {W}x{H}x{D}")
+
+
+def test_mixed_mode_full_size_c4_against_exact():
+    """C4: MIXED vs EXACT on the same device volumes: |dq| and the disparity maps."""
+    W, H, D = 1920, 1080, 128
+    l8, r8, _ = synth.stereo_pair_u8(W, H, D)
+    rng = np.random.default_rng(4)
+    r8 = np.clip(r8.astype(np.int16) + rng.integers(-5, 6, r8.shape), 0, 255).astype(np.uint8)
+    maps, slices = {}, {}
+    for mode in (capi.PSM_CVF_EXACT, capi.PSM_CVF_MIXED):
+        with DispEst(l8, r8, D) as de:
+            de.set_option(capi.PSM_OPT_CVF_MODE, mode)
+            de.CostConst_GPU(); de.CostFilter_GPU()
+            slices[mode] = [de.read_cost_slice(0, d) for d in (1, 40, 127)]
+            de.DispSelect_GPU()
+            maps[mode] = (de.lDisMap.copy(), de.rDisMap.copy())
+    for a, b in zip(slices[capi.PSM_CVF_EXACT], slices[capi.PSM_CVF_MIXED]):
+        assert np.max(np.abs(a - b)) <= 1e-5
+    for a, b in zip(maps[capi.PSM_CVF_EXACT], maps[capi.PSM_CVF_MIXED]):
+        diff = np.abs(a.astype(np.int16) - b.astype(np.int16))
+        assert int((diff > 1).sum()) == 0, (int((diff > 1).sum()), np.argwhere(diff > 1)[:5].tolist())
+        print("C4 mixed vs exact: +-1 flips", int((diff == 1).sum()), "of", diff.size)
+
+
+def test_full_size_c3_bit_exact(oracle):
+    """BASELINE config C3 (synthetic 1280x720, D=64) at FULL size: both filtered volumes and both maps
+    against the oracle (noise added so that costs are not trivially zero)."""
+    W, H, D = 1280, 720, 64
+    l8, r8, _ = synth.stereo_pair_u8(W, H, D)
+    rng = np.random.default_rng(33)
+    r8 = np.clip(r8.astype(np.int16) + rng.integers(-4, 5, r8.shape), 0, 255).astype(np.uint8)
+    l, r = synth.to_f32(l8), synth.to_f32(r8)
+    ref = oracle.pipeline(l, r, D, threads=64, keep_volumes=True)
+    g = run_gpu(l, r, D)
+    assert_same(g["lf"], ref["lVol"], "C3 left filtered volume")
+    assert_same(g["rf"], ref["rVol"], "C3 right filtered volume")
+    assert_same(g["ld"], ref["lDis"], "C3 lDisMap")
+    assert_same(g["rd"], ref["rDis"], "C3 rDisMap")
