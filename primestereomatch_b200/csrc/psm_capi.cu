@@ -200,15 +200,34 @@ int launch_cvf_stream(psm_ctx* c)
     }
     if (c->cvf_target_rows > 0) target_rows = c->cvf_target_rows;
     plan_segments(c->H, target_rows, &P.nseg, &P.seg_rows);
-    const size_t smem = (size_t)8 * 4 * nthreads * sizeof(float4) + (size_t)c->cvf_extra_smem;
     // kernel selection: mode (exact / mixed) x tuning variant (PSM option 100)
-    //   exact: 0 = integer widening (shipped), 1 = F2F conversions everywhere (round-1 kernel, kept as the A/B baseline)
-    //   mixed: 0 = <=168 registers, 1 = <=128 registers (more resident warps when the ring allows)
+    //   variant 0 (shipped): integer widening + history ring in tensor memory
+    //   variant 1: F2F conversions, ring in shared memory (the round-1 kernel, kept as the A/B baseline; exact only)
+    //   variant 2: integer widening, ring in shared memory
+    //   variant 3: F2F conversions, ring in tensor memory (exact only)
+    //   variant 4: as 0 with <= 128 registers (4 CTAs of 128 threads per SM)
     using kern_t = void (*)(CvfParams);
     kern_t kern = nullptr;
-    if (c->cvf_mode == PSM_CVF_MIXED) kern = c->cvf_variant == 1 ? cvf_stream_kernel<4, 1, kS2Mixed> : cvf_stream_kernel<3, 1, kS2Mixed>;
-    else kern = c->cvf_variant == 1 ? cvf_stream_kernel<3, 0, kS2Exact> : cvf_stream_kernel<3, 1, kS2Exact>;
+    bool tm = true;
+    if (c->cvf_mode == PSM_CVF_MIXED) {
+        switch (c->cvf_variant) {
+        case 2: kern = cvf_stream_kernel<3, 1, kS2Mixed, 0>; tm = false; break;
+        case 4: kern = cvf_stream_kernel<4, 1, kS2Mixed, 1>; break;
+        default: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1>; break;
+        }
+    } else {
+        switch (c->cvf_variant) {
+        case 1: kern = cvf_stream_kernel<3, 0, kS2Exact, 0>; tm = false; break;
+        case 2: kern = cvf_stream_kernel<3, 1, kS2Exact, 0>; tm = false; break;
+        case 3: kern = cvf_stream_kernel<3, 0, kS2Exact, 1>; break;
+        case 4: kern = cvf_stream_kernel<4, 1, kS2Exact, 1>; break;
+        default: kern = cvf_stream_kernel<3, 1, kS2Exact, 1>; break;
+        }
+    }
+    const size_t smem = (tm ? 0 : (size_t)8 * 4 * nthreads * sizeof(float4)) + (size_t)c->cvf_extra_smem;
     PSM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (tm && !c->cvf_extra_smem)  // nothing lives in shared memory: give the whole array to L1 (the guide rows are re-read by every slice)
+        PSM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
     P.guide_flags = c->guide_flags;
     const unsigned grid = 2u * P.nseg * P.nstrips * P.ndgroups;
     kern<<<grid, nthreads, smem, c->stream>>>(P);

@@ -154,14 +154,54 @@ __device__ __forceinline__ f2x2 hsum8f(const f2x2& c)
     return h;
 }
 
+
+// ---- a,b / pair history ring in TENSOR MEMORY ---------------------------------------------------
+// The ring (8 slots x 4 planes x 4 columns per thread = 128 words per thread, 16 KB per warp) is the
+// only per-slice on-chip history and was what capped the kernel at 12 warps per SM when it lived in
+// shared memory (192 KB of rings left ~35 KB of L1 for the guide rows).  On sm_100a each SM has
+// 256 KB of tensor memory (512 columns x 128 lanes x 32 bit) that this kernel does not need for
+// MMA accumulators, and tcgen05.ld/st in the 32x32b shape give every thread of a warp a private
+// row: lane i of warp w addresses TMEM lane 32*(w%4)+i.  One ring = 128 columns of one lane quarter;
+// a CTA allocates 128 columns for its <= 4 warps.  One LDTM / STTM moves a whole slot (16 words per
+// thread) -- 4x fewer instructions than LDS/STS.128 -- and shared memory / L1 is left to the loads.
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, f2x2 (&v)[4])
+{
+    unsigned r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        v[q] = {make_float2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])),
+                make_float2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]))};
+}
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const f2x2 (&v)[4])
+{
+    unsigned r[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        r[4 * q] = __float_as_uint(v[q].lo.x); r[4 * q + 1] = __float_as_uint(v[q].lo.y);
+        r[4 * q + 2] = __float_as_uint(v[q].hi.x); r[4 * q + 3] = __float_as_uint(v[q].hi.y);
+    }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+constexpr unsigned kTmemCols = 128;   // columns per CTA: one 128-column ring per lane quarter (warp)
+
 // MINB: resident CTAs per SM the register allocation is sized for (3 -> <=168 regs, 4 -> <=128);
 // IW  : 1 = integer widening into the scaled domain (stage 1, and stage 2 when exact), 0 = F2F everywhere
 // S2M : kS2Exact / kS2Mixed
-template <int MINB, int IW, int S2M>
+// TM  : 1 = history ring in tensor memory (tcgen05.ld/st), 0 = in shared memory
+template <int MINB, int IW, int S2M, int TM>
 __global__ void __launch_bounds__(kCvfMaxThreads, MINB)
 cvf_stream_kernel(const CvfParams P)
 {
-    extern __shared__ float4 ring[];  // [8 slots][4 planes][blockDim.x threads]
+    extern __shared__ float4 ring[];  // TM == 0: [8 slots][4 planes][blockDim.x threads]
+    __shared__ unsigned tmem_base_smem;
     constexpr bool MIXED = (S2M == kS2Mixed);
     constexpr double kMean1 = IW ? kMeanScaled : kMeanPlain;   // stage-1 mean scale
     constexpr double kMean2 = IW ? kMeanScaled : kMeanPlain;   // stage-2 (exact) mean scale
@@ -183,8 +223,27 @@ cvf_stream_kernel(const CvfParams P)
     const int strip = b % P.nstrips;   b /= P.nstrips;
     const int seg = b % P.nseg;
     const int view = b / P.nseg;
-    const int dlc = dgroup * wpc + warp;
-    if (dlc >= P.Dloc) return;  // warps never synchronise with each other
+    const int dlc_raw = dgroup * wpc + warp;
+    const bool active = dlc_raw < P.Dloc;
+    const int dlc = active ? dlc_raw : P.Dloc - 1;
+    unsigned tring = 0;   // TMEM address of this warp's ring (lane quarter = warp % 4, column 0 of the CTA's allocation)
+    if (TM) {
+        // one warp allocates the CTA's columns, everybody reads the base after a fenced barrier; this
+        // barrier and the one before the deallocation are the only CTA-wide synchronisations
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"((unsigned)__cvta_generic_to_shared(&tmem_base_smem)), "r"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tring = tmem_base_smem + ((unsigned)(warp & 3) << 21);   // lane field = bits 31..16: (warp%4)*32 << 16
+    } else if (!active) {
+        return;  // warps never synchronise with each other
+    }
+    // TM: a surplus warp of the last slice group (Dloc % wpc != 0) redoes the last slice with its stores
+    // masked, so that every warp reaches the barrier before the deallocation without a divergent region
 
     const int W = P.W, H = P.H;
     const unsigned Wp = (unsigned)P.Wp;
@@ -199,7 +258,7 @@ cvf_stream_kernel(const CvfParams P)
     const char* __restrict__ vin = reinterpret_cast<const char*>(P.vol_in[view] + (size_t)dlc * plane + cin);
     char* __restrict__ vout = reinterpret_cast<char*>(P.vol_out[view] + (size_t)dlc * plane + cin + 8);
     const size_t planeB = (size_t)plane * 4, rowB = (size_t)Wp * 4;
-    const bool store_ok = lane <= 27 && cin + 8 < W && cin + 8 >= out_lo;
+    const bool store_ok = active && lane <= 27 && cin + 8 < W && cin + 8 >= out_lo;
 
     // a guide with negative / non-finite values (outside the [0,1] image contract) disables the
     // integer widening for the whole launch of this view; `slow` also turns sticky once a row of p
@@ -242,6 +301,24 @@ cvf_stream_kernel(const CvfParams P)
 #pragma unroll
         for (int q = 0; q < 4; ++q) prev[q] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     }
+
+    // history ring accessors (slot = 0..7): a whole slot = 4 planes x 4 columns of this thread
+    auto ring_ld = [&](int slot, f2x2 (&v)[4]) {
+        if (TM) tmem_ld16(tring + (unsigned)slot * 16u, v);
+        else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = from4(ring[(slot * 4 + q) * nthr + tid]);
+        }
+    };
+    auto ring_st = [&](int slot, const f2x2 (&v)[4]) {
+        if (TM) tmem_st16(tring + (unsigned)slot * 16u, v);
+        else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ring[(slot * 4 + q) * nthr + tid] = to4(v[q]);
+        }
+    };
+    auto ring_wait_ld = [&]() { if (TM) tmem_wait_ld(); };
+    auto ring_wait_st = [&]() { if (TM) tmem_wait_st(); };
 
     struct RowIn { float4 p, i0, i1, i2; };
     auto load_at = [&](size_t ro) {  // ro: byte offset of the row
@@ -406,30 +483,34 @@ cvf_stream_kernel(const CvfParams P)
         const bool warm = top ? (t <= 4) : (age < 8);
         const bool first_out = top ? (t == 4) : (age == 7);
         if (!MIXED) {
+            ring_wait_st();
             if (!real_row) {  // virtual a,b row below the image == reflected row, still in the ring
-                const int slot = reflect101(t, H) & 7;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) av[q] = from4(ring[(slot * 4 + q) * nthr + tid]);
+                ring_ld(reflect101(t, H) & 7, av);
+                ring_wait_ld();
             }
             const double wnew = (top && t >= 1 && t <= 3) ? 2.0 : 1.0;      // rows 1..3 appear twice in row 0's window
             const int oslot = (top && t < 8) ? ((8 - t) & 7) : (t & 7);      // slot of a,b row reflect(t-8)
             const int nslot = t & 7;
+            f2x2 old[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) old[q] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            if (!warm) { ring_ld(oslot, old); ring_wait_ld(); }
+            if (real_row) ring_st(nslot, av);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float4 old4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (!warm) old4 = ring[(oslot * 4 + q) * nthr + tid];
-                if (real_row) ring[(nslot * 4 + q) * nthr + tid] = to4(av[q]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     double s = __fma_rn(wnew, w2(get(av[q], j), slow), S2[MIXED ? 0 : q][j]);  // exact: wnew is 1 or 2
-                    if (!warm) s = __dsub_rn(s, w2(comp(old4, j), slow));
+                    if (!warm) s = __dsub_rn(s, w2(get(old[q], j), slow));
                     S2[MIXED ? 0 : q][j] = s;
                 }
             }
         } else if (real_row) {
             if (t > T0) {  // pair(t) = ab(t-1) + ab(t); the first row of a segment has no predecessor
+                f2x2 pr[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) ring[((t & 7) * 4 + q) * nthr + tid] = to4(add2(av[q], prev[q]));
+                for (int q = 0; q < 4; ++q) pr[q] = add2(av[q], prev[q]);
+                ring_st(t & 7, pr);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) prev[q] = av[q];
@@ -445,14 +526,12 @@ cvf_stream_kernel(const CvfParams P)
                 emit(ro, o0, o1, o2);
             } else {
                 f2x2 pa[4], pb[4], pc[4], pd[4];
-                const int sa = refl_p(y - 3) & 7, sb = refl_p(y - 1) & 7, sc = refl_p(y + 1) & 7, sd = refl_p(y + 3) & 7;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    pa[q] = from4(ring[(sa * 4 + q) * nthr + tid]);
-                    pb[q] = from4(ring[(sb * 4 + q) * nthr + tid]);
-                    pc[q] = from4(ring[(sc * 4 + q) * nthr + tid]);
-                    pd[q] = from4(ring[(sd * 4 + q) * nthr + tid]);
-                }
+                ring_wait_st();
+                ring_ld(refl_p(y - 3) & 7, pa);
+                ring_ld(refl_p(y - 1) & 7, pb);
+                ring_ld(refl_p(y + 1) & 7, pc);
+                ring_ld(refl_p(y + 3) & 7, pd);
+                ring_wait_ld();
                 emit_pairs(ro, pa, pb, pc, pd, o0, o1, o2);
             }
         }
@@ -501,32 +580,29 @@ cvf_stream_kernel(const CvfParams P)
             }
             if (!MIXED) {
                 // stage 2 (exact) of a,b row t (output row t-3): ring exchange, S2 update, q
-                float4* rp = ring + ((t & 7) * 4) * nthr + tid;
+                f2x2 old[4];
+                ring_wait_st();
+                ring_ld(t & 7, old);
+                ring_wait_ld();
+                ring_st(t & 7, av);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float4 old4 = rp[q * nthr];
-                    rp[q * nthr] = to4(av[q]);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        S2[MIXED ? 0 : q][j] = __dsub_rn(__dadd_rn(S2[MIXED ? 0 : q][j], w2(get(av[q], j), SLOW)), w2(comp(old4, j), SLOW));
+                        S2[MIXED ? 0 : q][j] = __dsub_rn(__dadd_rn(S2[MIXED ? 0 : q][j], w2(get(av[q], j), SLOW)), w2(get(old[q], j), SLOW));
                 }
                 emit(ro_y, o0, o1, o2);
             } else {
                 // stage 2 (mixed): pair(t) into the ring, window = (pair(t-6)+pair(t-4)) + (pair(t-2)+pair(t))
                 f2x2 pa[4], pb[4], pc[4], pd[4];
-                const float4* r6 = ring + (((t - 6) & 7) * 4) * nthr + tid;
-                const float4* r4 = ring + (((t - 4) & 7) * 4) * nthr + tid;
-                const float4* r2 = ring + (((t - 2) & 7) * 4) * nthr + tid;
-                float4* r0 = ring + ((t & 7) * 4) * nthr + tid;
+                ring_wait_st();
+                ring_ld((t - 6) & 7, pa);
+                ring_ld((t - 4) & 7, pb);
+                ring_ld((t - 2) & 7, pc);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    pa[q] = from4(r6[q * nthr]);
-                    pb[q] = from4(r4[q * nthr]);
-                    pc[q] = from4(r2[q * nthr]);
-                    pd[q] = add2(av[q], prev[q]);
-                    r0[q * nthr] = to4(pd[q]);
-                    prev[q] = av[q];
-                }
+                for (int q = 0; q < 4; ++q) { pd[q] = add2(av[q], prev[q]); prev[q] = av[q]; }
+                ring_wait_ld();
+                ring_st(t & 7, pd);
                 emit_pairs(ro_y, pa, pb, pc, pd, o0, o1, o2);
             }
             ro_y += rowB;
@@ -540,6 +616,13 @@ cvf_stream_kernel(const CvfParams P)
         for (; t <= Ts1; ++t) steady(std::true_type{});
     }
     for (; t <= Tend; ++t) generic_step(t);
+    if (TM) {
+        tmem_wait_st();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_smem), "r"(kTmemCols) : "memory");
+    }
 }
 
 }  // namespace psm

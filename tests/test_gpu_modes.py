@@ -1,5 +1,6 @@
 """GPU tests of the CVF kernel's modes and paths (all through the C-ABI):
-  * PSM_CVF_EXACT with integer widening (shipped) and with F2F conversions (round-1 kernel) -- both bit-exact;
+  * PSM_CVF_EXACT in its four builds (integer widening / F2F conversions x history ring in tensor memory / in
+    shared memory; variant 0 is shipped, variant 1 is the round-1 kernel) -- all bit-exact;
   * inputs outside the integer-widening domain (negative / -0 costs, negative guide values) -- bit-exact through
     the per-row slow path and the guide flag;
   * PSM_CVF_MIXED -- bit-exact against its CPU model (tests/mixed_model.py), within tolerance of the exact path;
@@ -14,7 +15,7 @@ from test_gpu_parity import assert_same, run_gpu
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_exact_variants_bit_exact(variant, scenes, oracle_scene_results):
     _, _, l, r = scenes["Teddy"]
     ref = oracle_scene_results["Teddy"]
