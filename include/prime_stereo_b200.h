@@ -101,6 +101,18 @@ int psm_set_images_u8(psm_ctx* ctx, const uint8_t* left, size_t left_step,
 int psm_set_images_device(psm_ctx* ctx, const float* d_left, size_t left_step,
                           const float* d_right, size_t right_step);
 
+/* Pipelined upload (extension; the reference's DispEst is synchronous per frame): start the H2D copy
+ * of the NEXT frame on the context's copy stream into a second staging set while the current frame
+ * is still being computed, then make it the current frame.  Host buffers must be page-locked for the
+ * copy to overlap and must stay valid until psm_set_images_commit has returned.
+ *   psm_set_images_async(k+1) ... stages of frame k ... psm_set_images_commit()  ->  frame k+1 is current
+ * commit = compute stream waits for the upload, then the same ingest kernels as psm_set_images. */
+int psm_set_images_async(psm_ctx* ctx, const float* left, size_t left_step,
+                         const float* right, size_t right_step);
+int psm_set_images_u8_async(psm_ctx* ctx, const uint8_t* left, size_t left_step,
+                            const uint8_t* right, size_t right_step);
+int psm_set_images_commit(psm_ctx* ctx);
+
 /* Stage 1: both raw cost volumes (CostConst_GPU). Asynchronous on the context stream. */
 int psm_cost_const(psm_ctx* ctx);
 
@@ -112,6 +124,11 @@ int psm_cost_filter(psm_ctx* ctx);
  * (row steps in bytes) and synchronises (DispSelect_GPU).  Only valid on an unsharded context. */
 int psm_disp_select(psm_ctx* ctx, uint8_t* left, size_t left_step,
                     uint8_t* right, size_t right_step);
+
+/* Stage 3 with the D2H copies enqueued but NOT synchronised: the host maps are valid after psm_sync
+ * (or any later synchronising call).  Page-locked host memory keeps the call asynchronous. */
+int psm_disp_select_async(psm_ctx* ctx, uint8_t* left, size_t left_step,
+                          uint8_t* right, size_t right_step);
 
 /* Stage 3 without the D2H copy: maps stay on the device (see psm_device_ptr). Asynchronous. */
 int psm_disp_select_device(psm_ctx* ctx);

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libprime_stereo_b200.so")
 SYMBOLS = [
     "psm_device_count", "psm_create", "psm_create_sharded", "psm_destroy", "psm_set_option",
     "psm_set_stream", "psm_set_images", "psm_set_images_u8", "psm_set_images_device",
+    "psm_set_images_async", "psm_set_images_u8_async", "psm_set_images_commit", "psm_disp_select_async",
     "psm_cost_const", "psm_cost_filter", "psm_disp_select", "psm_disp_select_device",
     "psm_disp_select_keys", "psm_disp_reduce_keys", "psm_p2p_create_buffer", "psm_ipc_export", "psm_ipc_import",
     "psm_p2p_set_peers", "psm_disp_select_keys_p2p", "psm_disp_reduce_p2p", "psm_disp_fetch_p2p", "psm_read_cost_slice", "psm_write_cost_slice",
@@ -55,6 +56,10 @@ def lib():
     L.psm_set_images.argtypes = [vp, fp, sz, fp, sz]
     L.psm_set_images_u8.argtypes = [vp, u8p, sz, u8p, sz]
     L.psm_set_images_device.argtypes = [vp, fp, sz, fp, sz]
+    L.psm_set_images_async.argtypes = [vp, fp, sz, fp, sz]
+    L.psm_set_images_u8_async.argtypes = [vp, u8p, sz, u8p, sz]
+    L.psm_set_images_commit.argtypes = [vp]
+    L.psm_disp_select_async.argtypes = [vp, u8p, sz, u8p, sz]
     L.psm_cost_const.argtypes = [vp]
     L.psm_cost_filter.argtypes = [vp]
     L.psm_disp_select.argtypes = [vp, u8p, sz, u8p, sz]

@@ -20,7 +20,7 @@ namespace {
 
 constexpr int kNumStages = 5;  // ingest, cvc, cvf, wta, cvf-filter-kernel
 
-char g_create_error[512] = "";
+thread_local char g_create_error[512] = "";  // per host thread: psm_last_error(NULL) reports the calling thread's last failed creation
 
 }  // namespace
 
@@ -32,7 +32,14 @@ struct psm_ctx {
     float* grd[2] = {nullptr, nullptr};
     float* vol[2] = {nullptr, nullptr};     // current volumes (raw after CVC, filtered after CVF)
     float* vol_alt[2] = {nullptr, nullptr}; // the other half of the ping-pong
-    void* stage_in[2] = {nullptr, nullptr}; // device staging for the interleaved upload
+    void* stage_in[2] = {nullptr, nullptr}; // device staging for the interleaved upload (the set the synchronous calls use)
+    void* stage_alt[2] = {nullptr, nullptr};// second staging set: psm_set_images_async uploads frame k+1 while frame k is in flight
+    cudaStream_t copy_stream = nullptr;     // H2D stream of the asynchronous upload
+    cudaEvent_t up_done = nullptr;          // async upload finished (recorded on copy_stream)
+    cudaEvent_t ingest_done[2] = {nullptr, nullptr};  // ingest kernels consumed staging set k (recorded on the compute stream)
+    bool ingest_done_valid[2] = {false, false};
+    int stage_cur = 0;                      // staging set holding the current frame: 0 = stage_in, 1 = stage_alt
+    int up_pending = 0;                     // 0 none, 1 f32 upload pending, 2 u8 upload pending
     uint8_t* dis[2] = {nullptr, nullptr};
     int* guide_flags = nullptr;             // [2] device flags: guide outside the integer-widening domain (see psm_cvf_stream.cuh)
     unsigned char* p2p_own = nullptr;       // own exchange block: keys [2 views][nranks][chunk] u64 + maps [2 views][H*W] u8
@@ -46,7 +53,7 @@ struct psm_ctx {
     cudaEvent_t ev0[kNumStages] = {}, ev1[kNumStages] = {};
     bool ev_valid[kNumStages] = {};
     int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0, cvf_target_rows = 0, cvf_extra_smem = 0, cvf_threads = 0, cvf_remap = 0;
-    bool have_images = false, guide_valid = false, have_cvc = false;
+    bool have_images = false, guide_valid = false, have_cvc = false, filtered = false;
     uint64_t launches = 0;
     char err[512] = "";
 };
@@ -104,6 +111,8 @@ int pad_rows(psm_ctx* c, float* base, size_t nrows)
     return PSM_OK;
 }
 
+void* stage_buf(psm_ctx* c, int set, int view) { return set ? c->stage_alt[view] : c->stage_in[view]; }
+
 template <typename T>
 int ingest(psm_ctx* c, const T* l, size_t lstep, const T* r, size_t rstep, bool from_device)
 {
@@ -116,9 +125,9 @@ int ingest(psm_ctx* c, const T* l, size_t lstep, const T* r, size_t rstep, bool 
         const T* dsrc = src[v];
         size_t dstep = step[v];
         if (!from_device) {
-            PSM_CUDA(c, cudaMemcpy2DAsync(c->stage_in[v], row_bytes, src[v], step[v], row_bytes, c->H,
+            PSM_CUDA(c, cudaMemcpy2DAsync(stage_buf(c, c->stage_cur, v), row_bytes, src[v], step[v], row_bytes, c->H,
                                           cudaMemcpyHostToDevice, c->stream));
-            dsrc = static_cast<const T*>(c->stage_in[v]);
+            dsrc = static_cast<const T*>(stage_buf(c, c->stage_cur, v));
             dstep = row_bytes;
         }
         float* g = c->guide[v];
@@ -131,6 +140,30 @@ int ingest(psm_ctx* c, const T* l, size_t lstep, const T* r, size_t rstep, bool 
     c->have_images = true;
     c->guide_valid = false;
     c->have_cvc = false;
+    c->filtered = false;
+    return PSM_OK;
+}
+
+// asynchronous upload of the NEXT frame into the staging set that is not in use (copy stream)
+template <typename T>
+int upload_async(psm_ctx* c, const T* l, size_t lstep, const T* r, size_t rstep)
+{
+    const T* src[2] = {l, r};
+    const size_t step[2] = {lstep, rstep};
+    const size_t row_bytes = (size_t)c->W * 3 * sizeof(T);
+    if (c->up_pending) return fail(c, PSM_ESTATE, "an asynchronous upload is already pending: call psm_set_images_commit first");
+    const int set = c->stage_cur ^ 1;
+    if (!c->stage_alt[0]) {  // allocated on first use: synchronous callers never pay for the second set
+        for (int v = 0; v < 2; ++v) PSM_CUDA(c, cudaMalloc(&c->stage_alt[v], (size_t)c->W * c->H * 3 * sizeof(float)));
+    }
+    if (c->ingest_done_valid[set]) PSM_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ingest_done[set], 0));
+    for (int v = 0; v < 2; ++v) {
+        if (!src[v] || step[v] < row_bytes) return fail(c, PSM_EINVAL, "bad image pointer/step for view %d", v);
+        PSM_CUDA(c, cudaMemcpy2DAsync(stage_buf(c, set, v), row_bytes, src[v], step[v], row_bytes, c->H,
+                                      cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    PSM_CUDA(c, cudaEventRecord(c->up_done, c->copy_stream));
+    c->up_pending = sizeof(T) == 1 ? 2 : 1;
     return PSM_OK;
 }
 
@@ -213,6 +246,8 @@ int launch_cvf_stream(psm_ctx* c)
         switch (c->cvf_variant) {
         case 2: kern = cvf_stream_kernel<3, 1, kS2Mixed, 0>; tm = false; break;
         case 4: kern = cvf_stream_kernel<4, 1, kS2Mixed, 1>; break;
+        case 5: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1, 1>; break;
+        case 6: kern = cvf_stream_kernel<4, 1, kS2Mixed, 1, 1>; break;
         default: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1>; break;
         }
     } else {
@@ -221,6 +256,9 @@ int launch_cvf_stream(psm_ctx* c)
         case 2: kern = cvf_stream_kernel<3, 1, kS2Exact, 0>; tm = false; break;
         case 3: kern = cvf_stream_kernel<3, 0, kS2Exact, 1>; break;
         case 4: kern = cvf_stream_kernel<4, 1, kS2Exact, 1>; break;
+        case 5: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 1>; break;
+        case 6: kern = cvf_stream_kernel<3, 2, kS2Exact, 1, 0>; break;
+        case 7: kern = cvf_stream_kernel<3, 2, kS2Exact, 1, 1>; break;
         default: kern = cvf_stream_kernel<3, 1, kS2Exact, 1>; break;
         }
     }
@@ -317,6 +355,9 @@ int psm_create_sharded(psm_ctx** out, int width, int height, int max_disp, int d
     }
     PSM_CREATE_CUDA(cudaMalloc(&c->guide_flags, 2 * sizeof(int)));
     PSM_CREATE_CUDA(cudaMemsetAsync(c->guide_flags, 0, 2 * sizeof(int), c->stream));
+    PSM_CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    PSM_CREATE_CUDA(cudaEventCreateWithFlags(&c->up_done, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) PSM_CREATE_CUDA(cudaEventCreateWithFlags(&c->ingest_done[k], cudaEventDisableTiming));
     for (int s = 0; s < kNumStages; ++s) {
         PSM_CREATE_CUDA(cudaEventCreate(&c->ev0[s]));
         PSM_CREATE_CUDA(cudaEventCreate(&c->ev1[s]));
@@ -340,7 +381,11 @@ int psm_destroy(psm_ctx* c)
     for (int i = 0; i < c->p2p_nimported; ++i) cudaIpcCloseMemHandle(c->p2p_imported[i]);
     cudaFree(c->p2p_own);
     for (int i = 0; i < c->nalloc; ++i) cudaFree(c->alloc[i]);
-    for (int v = 0; v < 2; ++v) { cudaFree(c->stage_in[v]); cudaFree(c->dis[v]); }
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    for (int v = 0; v < 2; ++v) { cudaFree(c->stage_in[v]); cudaFree(c->stage_alt[v]); cudaFree(c->dis[v]); }
+    if (c->up_done) cudaEventDestroy(c->up_done);
+    for (int k = 0; k < 2; ++k) if (c->ingest_done[k]) cudaEventDestroy(c->ingest_done[k]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->ab);
     cudaFree(c->guide_flags);
     for (int s = 0; s < kNumStages; ++s) {
@@ -422,6 +467,39 @@ int psm_set_images_device(psm_ctx* c, const float* d_left, size_t left_step, con
     return stage_end(c, 0);
 }
 
+int psm_set_images_async(psm_ctx* c, const float* left, size_t left_step, const float* right, size_t right_step)
+{
+    if (int rc = bind(c)) return rc;
+    return upload_async<float>(c, left, left_step, right, right_step);
+}
+
+int psm_set_images_u8_async(psm_ctx* c, const uint8_t* left, size_t left_step, const uint8_t* right, size_t right_step)
+{
+    if (int rc = bind(c)) return rc;
+    return upload_async<uint8_t>(c, left, left_step, right, right_step);
+}
+
+int psm_set_images_commit(psm_ctx* c)
+{
+    if (int rc = bind(c)) return rc;
+    if (!c->up_pending) return fail(c, PSM_ESTATE, "psm_set_images_commit without a pending psm_set_images_async");
+    const int set = c->stage_cur ^ 1;
+    const bool u8 = c->up_pending == 2;
+    if (int rc = stage_begin(c, 0)) return rc;
+    PSM_CUDA(c, cudaStreamWaitEvent(c->stream, c->up_done, 0));
+    c->stage_cur = set;
+    c->up_pending = 0;
+    int rc;
+    if (u8) rc = ingest<uint8_t>(c, static_cast<const uint8_t*>(stage_buf(c, set, 0)), (size_t)c->W * 3,
+                                 static_cast<const uint8_t*>(stage_buf(c, set, 1)), (size_t)c->W * 3, true);
+    else rc = ingest<float>(c, static_cast<const float*>(stage_buf(c, set, 0)), (size_t)c->W * 3 * sizeof(float),
+                            static_cast<const float*>(stage_buf(c, set, 1)), (size_t)c->W * 3 * sizeof(float), true);
+    if (rc) return rc;
+    PSM_CUDA(c, cudaEventRecord(c->ingest_done[set], c->stream));
+    c->ingest_done_valid[set] = true;
+    return stage_end(c, 0);
+}
+
 int psm_cost_const(psm_ctx* c)
 {
     if (int rc = bind(c)) return rc;
@@ -445,6 +523,7 @@ int psm_cost_const(psm_ctx* c)
             if (int rc = pad_rows(c, c->vol[v], (size_t)c->d_count * c->H)) return rc;
     }
     c->have_cvc = true;
+    c->filtered = false;
     return stage_end(c, 1);
 }
 
@@ -476,6 +555,7 @@ int psm_cost_filter(psm_ctx* c)
     }
     for (int v = 0; v < 2; ++v) { float* t = c->vol[v]; c->vol[v] = c->vol_alt[v]; c->vol_alt[v] = t; }
     c->have_cvc = false;  // the volumes now hold filtered costs; filtering again needs a new CVC
+    c->filtered = true;
     return stage_end(c, 2);
 }
 
@@ -484,6 +564,7 @@ int psm_disp_select_device(psm_ctx* c)
     if (int rc = bind(c)) return rc;
     if (c->d_begin != 0 || c->d_count != c->D)
         return fail(c, PSM_ESTATE, "psm_disp_select on a sharded context: use psm_disp_select_keys + psm_disp_reduce_keys");
+    if (!c->filtered) return fail(c, PSM_ESTATE, "psm_disp_select before psm_cost_filter");
     if (int rc = stage_begin(c, 3)) return rc;
     for (int v = 0; v < 2; ++v) {
         dim3 blk(256), grd(((c->W + 3) / 4 + 255) / 256, c->H);
@@ -502,10 +583,18 @@ int psm_disp_select(psm_ctx* c, uint8_t* left, size_t left_step, uint8_t* right,
     return PSM_OK;
 }
 
+int psm_disp_select_async(psm_ctx* c, uint8_t* left, size_t left_step, uint8_t* right, size_t right_step)
+{
+    if (int rc = psm_disp_select_device(c)) return rc;
+    if (int rc = copy_map_out(c, c->dis[0], left, left_step)) return rc;
+    return copy_map_out(c, c->dis[1], right, right_step);
+}
+
 int psm_disp_select_keys(psm_ctx* c, uint64_t* d_keys_left, uint64_t* d_keys_right)
 {
     if (int rc = bind(c)) return rc;
     if (!d_keys_left || !d_keys_right) return fail(c, PSM_EINVAL, "null key buffer");
+    if (!c->filtered) return fail(c, PSM_ESTATE, "psm_disp_select_keys before psm_cost_filter");
     if (int rc = stage_begin(c, 3)) return rc;
     uint64_t* keys[2] = {d_keys_left, d_keys_right};
     for (int v = 0; v < 2; ++v) {
@@ -604,6 +693,7 @@ int psm_disp_select_keys_p2p(psm_ctx* c)
 {
     if (int rc = bind(c)) return rc;
     if (!c->p2p_own || !c->p2p_peer[0]) return fail(c, PSM_ESTATE, "psm_p2p_create_buffer / psm_p2p_set_peers first");
+    if (!c->filtered) return fail(c, PSM_ESTATE, "psm_disp_select_keys_p2p before psm_cost_filter");
     if (int rc = stage_begin(c, 3)) return rc;
     for (int v = 0; v < 2; ++v) {
         P2pPeers peers;

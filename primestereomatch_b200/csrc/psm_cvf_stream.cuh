@@ -131,6 +131,8 @@ __device__ __forceinline__ double widen_any(float f) { return __dmul_rn((double)
 
 __device__ __forceinline__ float4 ldg4(const char* __restrict__ p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+__device__ __forceinline__ void prefetch_l1(const char* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+
 __device__ __forceinline__ unsigned umax4(const float4& v)
 {
     return max(max(__float_as_uint(v.x), __float_as_uint(v.y)), max(__float_as_uint(v.z), __float_as_uint(v.w)));
@@ -193,10 +195,12 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 constexpr unsigned kTmemCols = 128;   // columns per CTA: one 128-column ring per lane quarter (warp)
 
 // MINB: resident CTAs per SM the register allocation is sized for (3 -> <=168 regs, 4 -> <=128);
-// IW  : 1 = integer widening into the scaled domain (stage 1, and stage 2 when exact), 0 = F2F everywhere
+// IW  : 0 = F2F everywhere; 1 = integer widening into the scaled domain in both stages; 2 = integer widening in
+//       stage 1 (non-negative values: one instruction each), F2F in the exact stage 2 (signed values would cost three)
 // S2M : kS2Exact / kS2Mixed
 // TM  : 1 = history ring in tensor memory (tcgen05.ld/st), 0 = in shared memory
-template <int MINB, int IW, int S2M, int TM>
+// PF  : 1 = prefetch the next step's guide rows into L1
+template <int MINB, int IW, int S2M, int TM, int PF = 0>
 __global__ void __launch_bounds__(kCvfMaxThreads, MINB)
 cvf_stream_kernel(const CvfParams P)
 {
@@ -204,7 +208,7 @@ cvf_stream_kernel(const CvfParams P)
     __shared__ unsigned tmem_base_smem;
     constexpr bool MIXED = (S2M == kS2Mixed);
     constexpr double kMean1 = IW ? kMeanScaled : kMeanPlain;   // stage-1 mean scale
-    constexpr double kMean2 = IW ? kMeanScaled : kMeanPlain;   // stage-2 (exact) mean scale
+    constexpr double kMean2 = IW == 1 ? kMeanScaled : kMeanPlain;   // stage-2 (exact) mean scale: IW == 2 keeps S2 unscaled
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int nthr = blockDim.x;
@@ -292,15 +296,10 @@ cvf_stream_kernel(const CvfParams P)
 
     double S1[4][4];
     double S2[MIXED ? 1 : 4][4];
-    f2x2 prev[MIXED ? 4 : 1];     // MIXED: a,b row t-1
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { S1[q][j] = 0.0; S2[MIXED ? 0 : q][j] = 0.0; }
-    if (MIXED) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) prev[q] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-    }
 
     // history ring accessors (slot = 0..7): a whole slot = 4 planes x 4 columns of this thread
     auto ring_ld = [&](int slot, f2x2 (&v)[4]) {
@@ -446,20 +445,17 @@ cvf_stream_kernel(const CvfParams P)
         }
         combine(ro, mb, i0, i1, i2);
     };
-    // MIXED: the four pair rows of one window -> q for one output row
-    auto emit_pairs = [&](size_t ro, const f2x2 (&pa)[4], const f2x2 (&pb)[4], const f2x2 (&pc)[4], const f2x2 (&pd)[4],
+    // MIXED: the two half-window sums  P(y-3)+P(y-1)  and  P(y+1)+P(y+3)  -> q for one output row
+    auto emit_pairs = [&](size_t ro, const f2x2 (&lo)[4], const f2x2 (&hi)[4],
                           const float4& i0, const float4& i1, const float4& i2) {
         f2x2 mb[4];
         const f2x2 k64 = {make_float2(1.f / 64.f, 1.f / 64.f), make_float2(1.f / 64.f, 1.f / 64.f)};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const f2x2 v = addp(addp(pa[q], pb[q]), addp(pc[q], pd[q]));  // (P(y-3)+P(y-1)) + (P(y+1)+P(y+3))
-            mb[q] = mul2(hsum8f(v), k64);
-        }
+        for (int q = 0; q < 4; ++q) mb[q] = mul2(hsum8f(addp(lo[q], hi[q])), k64);
         combine(ro, mb, i0, i1, i2);
     };
     // widening of a,b values for the exact stage 2
-    auto w2 = [&](float f, bool slow_now) { return !IW ? (double)f : (slow_now ? widen_any(f) : widen_sg(f)); };
+    auto w2 = [&](float f, bool slow_now) { return IW != 1 ? (double)f : (slow_now ? widen_any(f) : widen_sg(f)); };
 
     // MIXED: pair-row index with the row reflection folded in: P(s) = pair(refl_p(s))
     auto refl_p = [&](int s) { return s <= 0 ? 1 - s : (s >= H ? 2 * H - 1 - s : s); };
@@ -506,14 +502,18 @@ cvf_stream_kernel(const CvfParams P)
                 }
             }
         } else if (real_row) {
-            if (t > T0) {  // pair(t) = ab(t-1) + ab(t); the first row of a segment has no predecessor
+            // MIXED ring protocol: slot t&7 holds ab(t-1) until pair(t) = ab(t-1) + ab(t) replaces it; ab(t) waits in
+            // slot (t+1)&7, which is dead (pair(t-7) was last read at step t-1).  No a,b row lives in registers.
+            ring_wait_st();
+            if (t > T0) {  // the first row of a segment has no predecessor
                 f2x2 pr[4];
+                ring_ld(t & 7, pr);
+                ring_wait_ld();
 #pragma unroll
-                for (int q = 0; q < 4; ++q) pr[q] = add2(av[q], prev[q]);
+                for (int q = 0; q < 4; ++q) pr[q] = add2(av[q], pr[q]);
                 ring_st(t & 7, pr);
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) prev[q] = av[q];
+            ring_st((t + 1) & 7, av);
         }
         if (warm && !first_out) return;
         const int nrows = (top && t == 4) ? 2 : 1;  // output rows 0 and 1 share one reflected window
@@ -532,7 +532,9 @@ cvf_stream_kernel(const CvfParams P)
                 ring_ld(refl_p(y + 1) & 7, pc);
                 ring_ld(refl_p(y + 3) & 7, pd);
                 ring_wait_ld();
-                emit_pairs(ro, pa, pb, pc, pd, o0, o1, o2);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { pa[q] = addp(pa[q], pb[q]); pc[q] = addp(pc[q], pd[q]); }
+                emit_pairs(ro, pa, pc, o0, o1, o2);
             }
         }
     };
@@ -569,6 +571,12 @@ cvf_stream_kernel(const CvfParams P)
             {   // stage 1 of a,b row ro_t: S1 += newest, row sums -> a,b, S1 -= oldest; refills xn / xo
                 float4 g4[10];
                 load_guide(ro_t, g4);
+                if (PF) {   // next step's coefficient rows and output-column guide rows -> L1 (one step = thousands of cycles ahead)
+#pragma unroll
+                    for (int q = 0; q < 10; ++q) prefetch_l1(Ga + ((size_t)(kGuideMean + q) * planeB + ro_t + rowB));
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) prefetch_l1(Go + ((size_t)q * planeB + ro_y + rowB));
+                }
                 add_row(xn, SLOW);
                 ro_n += rowB;
                 xn = load_at(ro_n);     // into the registers add_row just released
@@ -598,12 +606,19 @@ cvf_stream_kernel(const CvfParams P)
                 ring_wait_st();
                 ring_ld((t - 6) & 7, pa);
                 ring_ld((t - 4) & 7, pb);
-                ring_ld((t - 2) & 7, pc);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { pd[q] = add2(av[q], prev[q]); prev[q] = av[q]; }
                 ring_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pa[q] = addp(pa[q], pb[q]);          // P(y-3) + P(y-1)
+                ring_ld((t - 2) & 7, pc);
+                ring_ld(t & 7, pd);                                              // ab(t-1)
+                ring_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pd[q] = add2(av[q], pd[q]);          // pair(t): scalar adds (av are products)
                 ring_st(t & 7, pd);
-                emit_pairs(ro_y, pa, pb, pc, pd, o0, o1, o2);
+                ring_st((t + 1) & 7, av);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pc[q] = addp(pc[q], pd[q]);          // P(y+1) + P(y+3)
+                emit_pairs(ro_y, pa, pc, o0, o1, o2);
             }
             ro_y += rowB;
         };

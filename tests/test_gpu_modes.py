@@ -15,7 +15,7 @@ from test_gpu_parity import assert_same, run_gpu
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 6])
 def test_exact_variants_bit_exact(variant, scenes, oracle_scene_results):
     _, _, l, r = scenes["Teddy"]
     ref = oracle_scene_results["Teddy"]
