@@ -4,16 +4,22 @@
 Contract (see the task brief): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line
 on rank 0.  A "step" is one stereo frame through CostConst_GPU + CostFilter_GPU + DispSelect_GPU
 producing BOTH disparity maps.  Workload at every N: BASELINE config C4, synthetic 1920x1080, D=128,
-fp32.  N>1 (launched by torchrun, one rank per GPU): the disparity axis is sharded D/N slices per
-rank, one NCCL all-gather of packed per-pixel (cost,d) minima per view, then the final min -> u8 maps
+fp32 (`--workload C3|C5` select the other synthetic BASELINE configs).  N>1 (launched by torchrun, one
+rank per GPU): the disparity axis is sharded D/N slices per rank; the one exchange of the path (per-pixel
+packed (cost,d) minima -> final maps) is a fused reduce-scatter + all-gather over NVLink peer memory
 (strong scaling: the frame is fixed, `value` = frames/s of the whole job).
 
-  value : frames/s with the interleaved f32 images already resident in HBM (device-timed, CUDA events)
-  e2e   : same metric through the host-facing C-ABI calls: images in pinned HOST memory, H2D of both
-          images and D2H of both u8 maps inside the timed region
-  roofline : the fused CVF kernel's algorithmic bytes / its event-timed duration vs the measured HBM peak
-  cpu_baseline / --impl reference : the CPU oracle (C restatement of the reference's pthreads path;
-          the reference itself cannot be built here: no OpenCV C++ headers / CL/cl.h) on the host cores
+  value    : frames/s with the interleaved f32 images already resident in HBM (device-timed, CUDA events)
+  e2e      : same metric through the host-facing C-ABI calls: frames in pinned HOST memory, the H2D copy of
+             every frame's two images and the D2H read of both u8 maps inside the timed region (the upload
+             of frame k+1 overlaps the computation of frame k: psm_set_images_async)
+  roofline : the fused CVF kernel's algorithmic bytes / its event-timed duration vs the measured HBM peak,
+             plus the pipe that actually limits it (from the committed ncu summary)
+  parity   : before the line is printed, the maps fetched by the last e2e step are compared with the CPU
+             oracle on a row band (exact mode: equal; mixed mode: +-1, flips counted)
+  cpu_baseline / --impl reference : the reference's pthreads CPU path on the host cores: oracle/_ref (the
+             reference's own CVC/CVF/DispSel sources compiled against an OpenCV shim) when it was built,
+             else the C port; a bounded slice sample per step, all cores and the reference's 8-thread cap
 """
 import argparse
 import ctypes as C
@@ -32,10 +38,14 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {  # BASELINE.json configs; C4 is the one the metric is quoted on and the default at every N
     "C3": (1280, 720, 64), "C4": (1920, 1080, 128), "C5": (1920, 1080, 256),
 }
-W, H, D = WORKLOADS["C4"]
-WORKLOAD = "C4 synthetic 1920x1080 D=128 fp32, both views (lDisMap+rDisMap)"
 METRIC = "disparity_volumes_per_s"
 UNIT = "volumes/s"
+MODES = ["exact", "mixed", "naive"]
+
+
+def workload_name(key):
+    W, H, D = WORKLOADS[key]
+    return f"{key} synthetic {W}x{H} D={D} fp32, both views (lDisMap+rDisMap)"
 
 
 def measured_peaks():
@@ -46,6 +56,16 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profile_facts(workload, mode):
+    """ncu-derived facts for THIS workload and mode from the committed summary (profiles/cvf_profile_facts.json):
+    DRAM traffic per launch and the limiting pipe.  None when that combination was never profiled."""
+    p = os.path.join(ROOT, "profiles", "cvf_profile_facts.json")
+    try:
+        return json.load(open(p)).get(f"{workload}:{mode}")
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -88,49 +108,81 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def oracle_frame(l, r, threads, sample_slices=None):
-    """One frame (or a slice sample of it) through the CPU oracle -> seconds per FULL frame."""
+# ------------------------------------------------------------------------------------------------------
+# CPU side (test infrastructure used as the reported baseline / the checker, never as the product path)
+# ------------------------------------------------------------------------------------------------------
+def cpu_backend():
+    """-> (kind, pipeline(l, r, D, threads) -> dict with times_ms)"""
+    from oracle import ref as R
+    if R.available():
+        return "reference", lambda l, r, D, threads: R.pipeline(l, r, D, threads=threads)
     from oracle import oracle as O
-    Ds = D if sample_slices is None else sample_slices
+    return "port", lambda l, r, D, threads: O.pipeline(l, r, D, threads=threads)
+
+
+def cpu_sample(run, l, r, D, threads, slices):
+    """CVC+CVF+WTA of the first `slices` disparity slices of both views on `threads` host threads
+    -> seconds extrapolated to the full frame (per-slice work is uniform; WTA is ~1 % of a frame)."""
     t0 = time.perf_counter()
-    res = O.pipeline(l, r, Ds, threads=threads)
+    res = run(l, r, slices, threads)
     dt = time.perf_counter() - t0
-    # per-slice cost is uniform (every slice is the same CVC + GIF work; WTA is 1% of the frame)
-    return dt * (D / Ds), res["times_ms"]
+    return dt * (D / slices), res["times_ms"]
+
+
+def cpu_report(l, r, D, workload, steps, warmup):
+    """The CPU arm: `steps` timed samples at all host cores (after `warmup`), plus one sample at the reference's
+    own cap of 8 threads (MAX_CPU_THREADS, include/ComFunc.h:52).  Sample = min(threads, D) slices per view so
+    that one batch of the reference's one-thread-per-slice scheduler is timed (DispEst.cpp:235-251)."""
+    kind, run = cpu_backend()
+    cores = os.cpu_count() or 1
+    th_all = min(cores, D)
+    s_all = min(D, max(th_all, 16))
+    for _ in range(warmup):
+        cpu_sample(run, l, r, D, th_all, s_all)
+    ts = [cpu_sample(run, l, r, D, th_all, s_all)[0] for _ in range(max(1, steps))]
+    sec = float(np.mean(ts))
+    th8 = min(8, cores)
+    sec8, _ = cpu_sample(run, l, r, D, th8, th8)
+    what = ("reference's own src/{CVC,CVF,DispSel}.cpp compiled against oracle/shim (oracle/_ref)" if kind == "reference"
+            else "C port of the reference path (oracle/libstereo_oracle.so; oracle/_ref not built)")
+    return {
+        "value": 1.0 / sec, "unit": UNIT, "cores": th_all, "kind": kind,
+        "sample": f"{s_all} of {D} disparity slices of both views of {workload} on {th_all} threads, scaled x{D / s_all:g}; {what}",
+        "host_cores": cores,
+        "capped_8_threads": {"value": 1.0 / sec8, "unit": UNIT, "cores": th8,
+                             "sample": f"{th8} of {D} slices on {th8} threads (the reference's MAX_CPU_THREADS cap), scaled x{D / th8:g}"},
+    }, sec
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU path (oracle port) on the host cores, rank 0 only."""
+    """--impl reference: the reference's CPU path on the host cores, rank 0 only."""
     if rank != 0:
         return
     from primestereomatch_b200 import synth
+    W, H, D = WORKLOADS[args.workload]
     l, r, _ = synth.stereo_pair_f32(W, H, D)
-    cores = os.cpu_count() or 1
-    threads = min(cores, D)
-    n = args.steps + args.warmup
-    # bounded sample: the whole frame when the run is short, else a D/8-slice sample of it
-    sample = None if n <= 8 else max(8, D // 8)
-    for _ in range(args.warmup):
-        oracle_frame(l, r, threads, sample)
-    ts = []
-    for _ in range(args.steps):
-        t, _ = oracle_frame(l, r, threads, sample)
-        ts.append(t)
-    sec = float(np.mean(ts))
+    cb, sec = cpu_report(l, r, D, workload_name(args.workload), args.steps, args.warmup)
     val = 1.0 / sec
-    what = "full frame" if sample is None else f"{sample} of {D} disparity slices of both views, scaled x{D / sample:g}"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "threads": threads,
-                   "note": "CPU oracle = C restatement of the reference pthreads path (reference needs OpenCV+OpenCL headers: unbuildable here); "
-                           "threads = all host cores (the reference itself caps at MAX_CPU_THREADS=8)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": what},
+        "config": {"workload": workload_name(args.workload)},
+        "cpu_baseline": cb,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def oracle_band_maps(l, r, D, y0, y1):
+    """Both disparity maps of rows [y0, y1) from the CPU oracle run on a row band with a 16-row margin (8 rows
+    of guide means + 8 of the two box stages reach into the neighbourhood; image borders reflect as in the frame)."""
+    from oracle import oracle as O
+    H = l.shape[0]
+    c0, c1 = max(0, y0 - 16), min(H, y1 + 16)
+    res = O.pipeline(np.ascontiguousarray(l[c0:c1]), np.ascontiguousarray(r[c0:c1]), D, threads=min(os.cpu_count() or 1, D))
+    return res["lDis"][y0 - c0:y1 - c0], res["rDis"][y0 - c0:y1 - c0]
 
 
 def main():
@@ -139,9 +191,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cvf-mode", type=int, default=0)
+    ap.add_argument("--cvf-mode", type=int, default=0, help="0 exact (default, the headline), 1 mixed (tolerance mode)")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS),
                     help="C4 (default) is the benchmark; C3 / C5 are the other synthetic BASELINE configs")
     ap.add_argument("--seg-rows", type=int, default=0)
@@ -151,13 +204,12 @@ def main():
     ap.add_argument("--upload", default="banded", choices=["banded", "replicated"],
                     help="N>1, e2e: banded = every rank uploads H/N rows of both images and the bands are "
                          "all-gathered over NVLink; replicated = every rank uploads both full images over PCIe")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1: p2p = WTA kernel stores its minima into every rank's buffer over NVLink (fused "
-                         "compute+exchange); nccl = local WTA then ncclAllGather")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "p2p-barrier", "nccl"],
+                    help="N>1: p2p = fused WTA + exchange over NVLink peer memory, ordered by device-side flags; "
+                         "p2p-barrier = same kernels separated by NCCL barriers; nccl = local WTA then ncclAllGather")
     args = ap.parse_args()
-    global W, H, D, WORKLOAD
     W, H, D = WORKLOADS[args.workload]
-    WORKLOAD = f"{args.workload} synthetic {W}x{H} D={D} fp32, both views (lDisMap+rDisMap)"
+    WORKLOAD = workload_name(args.workload)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -170,6 +222,7 @@ def main():
     import torch
     import torch.distributed as dist
     from primestereomatch_b200 import DispEst, capi, synth
+    from primestereomatch_b200.sharding import BandedUpload, P2PExchange, shard_range
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
@@ -189,10 +242,7 @@ def main():
     ld_dev, rd_dev = lp.cuda(), rp.cuda()
     torch.cuda.synchronize()
 
-    d_count = D // world
-    d_begin = rank * d_count
-    if rank == world - 1:
-        d_count = D - d_begin
+    d_begin, d_count = shard_range(D, world, rank)
     de = DispEst(l, r, D, 8, True, device=local_rank, d_begin=d_begin, d_count=d_count)
     de.set_option(capi.PSM_OPT_CVF_MODE, args.cvf_mode)
     de.set_option(capi.PSM_OPT_VARIANT, args.variant)
@@ -200,7 +250,7 @@ def main():
     de.set_option(102, args.extra_smem)
     de.set_option(103, args.cta_threads)
     de.set_option(104, args.remap)
-    stream = torch.cuda.Stream()  # a real (non-default) stream: handle 0 would mean "context's own stream"
+    stream = torch.cuda.Stream()  # a real (non-default) stream shared by the context and torch's collectives
     torch.cuda.set_stream(stream)
     capi.check(L.psm_set_stream(de.handle, C.c_void_p(stream.cuda_stream)), de.handle)
 
@@ -212,41 +262,20 @@ def main():
         keys = torch.empty((2, npix), dtype=torch.int64, device="cuda")
         gathered = torch.empty((2, world, npix), dtype=torch.int64, device="cuda")
     elif world > 1:
-        from primestereomatch_b200.sharding import P2PExchange
-        p2p = P2PExchange(de, world, rank)
+        p2p = P2PExchange(de, world, rank, device_sync=(args.exchange == "p2p"))
     step_bytes = W * 3 * 4
-    banded = world > 1 and args.upload == "banded"
-    if banded:  # row band of this rank (pinned host views) + device buffers for the band and the gathered images
-        rows = (H + world - 1) // world
-        r0, r1 = min(H, rank * rows), min(H, (rank + 1) * rows)
-        band_l = torch.zeros((rows, W, 3), dtype=torch.float32, device="cuda")
-        band_r = torch.zeros((rows, W, 3), dtype=torch.float32, device="cuda")
-        full_l = torch.empty((world * rows, W, 3), dtype=torch.float32, device="cuda")
-        full_r = torch.empty((world * rows, W, 3), dtype=torch.float32, device="cuda")
+    banded = BandedUpload(de, world, rank) if (world > 1 and args.upload == "banded") else None
 
-    def step(e2e):
-        if e2e == "u8":   # caller keeps 8-bit frames: StereoMatch.cpp:193-197's convertTo runs on the device
-            capi.check(L.psm_set_images_u8(de.handle, lp8.data_ptr(), W * 3, rp8.data_ptr(), W * 3), de.handle)
-        elif e2e and banded:
-            # each rank moves only its band over PCIe; NVLink all-gather completes the images on every GPU
-            band_l[: r1 - r0].copy_(lp[r0:r1], non_blocking=True)
-            band_r[: r1 - r0].copy_(rp[r0:r1], non_blocking=True)
-            dist.all_gather_into_tensor(full_l.view(-1), band_l.view(-1))
-            dist.all_gather_into_tensor(full_r.view(-1), band_r.view(-1))
-            capi.check(L.psm_set_images_device(de.handle, full_l.data_ptr(), step_bytes, full_r.data_ptr(), step_bytes), de.handle)
-        elif e2e:
-            capi.check(L.psm_set_images(de.handle, lp.data_ptr(), step_bytes, rp.data_ptr(), step_bytes), de.handle)
-        else:
-            capi.check(L.psm_set_images_device(de.handle, ld_dev.data_ptr(), step_bytes, rd_dev.data_ptr(), step_bytes), de.handle)
+    def finish(e2e):
+        """stages after the images are set: CVC, CVF, WTA (+ exchange), maps to host when e2e"""
         capi.check(L.psm_cost_const(de.handle), de.handle)
         capi.check(L.psm_cost_filter(de.handle), de.handle)
         if world == 1:
-            if e2e:
-                capi.check(L.psm_disp_select(de.handle, lmap.data_ptr(), W, rmap.data_ptr(), W), de.handle)
+            if e2e:  # D2H enqueued, not synchronised: the host maps are read after the timed region's final sync
+                capi.check(L.psm_disp_select_async(de.handle, lmap.data_ptr(), W, rmap.data_ptr(), W), de.handle)
             else:
                 capi.check(L.psm_disp_select_device(de.handle), de.handle)
         elif p2p is not None:
-            # WTA+scatter kernel, barrier, chunk-reduce+gather kernel, barrier (all over NVLink peer memory)
             p2p.frame(lmap.data_ptr() if e2e else None, rmap.data_ptr() if e2e else None)
         else:
             capi.check(L.psm_disp_select_keys(de.handle, keys[0].data_ptr(), keys[1].data_ptr()), de.handle)
@@ -257,19 +286,43 @@ def main():
             capi.check(L.psm_disp_reduce_keys(de.handle, gathered[0].data_ptr(), gathered[1].data_ptr(), world,
                                               out_l, W, out_r, W), de.handle)
 
+    def upload_async(e2e):
+        if e2e == "u8":
+            capi.check(L.psm_set_images_u8_async(de.handle, lp8.data_ptr(), W * 3, rp8.data_ptr(), W * 3), de.handle)
+        else:
+            capi.check(L.psm_set_images_async(de.handle, lp.data_ptr(), step_bytes, rp.data_ptr(), step_bytes), de.handle)
+
+    def run_steps(e2e, n):
+        """n frames.  Device-resident inputs (e2e False): ingest from HBM.  Host frames: at N=1 (and N>1 replicated)
+        a two-deep pipeline -- the H2D of frame k+1 runs on the copy stream while frame k computes; banded N>1:
+        band upload + NVLink all-gather per frame on the compute stream."""
+        if not e2e:
+            for _ in range(n):
+                capi.check(L.psm_set_images_device(de.handle, ld_dev.data_ptr(), step_bytes, rd_dev.data_ptr(), step_bytes), de.handle)
+                finish(False)
+        elif banded is not None and e2e != "u8":
+            for _ in range(n):
+                banded.upload(lp, rp)
+                finish(True)
+        else:
+            upload_async(e2e)                  # frame 0
+            for k in range(n):
+                capi.check(L.psm_set_images_commit(de.handle), de.handle)
+                if k + 1 < n:
+                    upload_async(e2e)          # frame k+1 uploads while frame k computes
+                finish(True)
+
     def timed(e2e, steps):
         """K steps bracketed by barrier + synchronize on both sides, CUDA events on the launching
         stream, max over ranks.  No host synchronisation inside the region."""
-        for _ in range(warm):
-            step(e2e)
+        run_steps(e2e, warm)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(steps):
-            step(e2e)
+        run_steps(e2e, steps)
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -285,7 +338,7 @@ def main():
         sync per step, which is why this is a separate loop from the throughput measurement."""
         out = []
         for _ in range(steps):
-            step(False)
+            run_steps(False, 1)
             out.append(de.stage_ms(4))
         return out
 
@@ -301,6 +354,26 @@ def main():
     e2e_ms = timed(True, args.steps)
     e2e_u8_ms = timed("u8", args.steps)
 
+    # ---- parity: the maps the last timed e2e step left in host memory vs the CPU oracle on a row band ----
+    parity = None
+    if not args.no_parity:
+        run_steps(True, 1)
+        torch.cuda.synchronize()
+        if rank == 0:
+            y0, y1 = H // 2 - 24, H // 2 + 24
+            wl, wr = oracle_band_maps(l, r, D, y0, y1)
+            gl, gr = lmap.numpy()[y0:y1], rmap.numpy()[y0:y1]
+            dl = np.abs(gl.astype(np.int16) - wl.astype(np.int16))
+            dr = np.abs(gr.astype(np.int16) - wr.astype(np.int16))
+            worst = int(max(dl.max(), dr.max()))
+            flips = int((dl > 0).sum() + (dr > 0).sum())
+            ok = worst == 0 if args.cvf_mode == 0 else worst <= 1
+            parity = {"checked": True, "ok": bool(ok), "rows": [y0, y1], "max_abs_disparity_diff": worst,
+                      "pixels_differing": flips, "against": "CPU oracle (oracle/libstereo_oracle.so) on the same frame",
+                      "rule": "equal" if args.cvf_mode == 0 else "+-1 disparity level"}
+            if not ok:
+                raise SystemExit(f"bench.py: PARITY FAILURE against the oracle: {parity}")
+
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = 1e3 / ms_per_step
@@ -310,42 +383,40 @@ def main():
         algo_bytes = 2 * (8 * V + 48 * W * H)  # one launch filters both views: read p + write q + 12 guide floats/px
         kern_ms = float(np.mean(kms))
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "cvf_traffic.json")
-        if world == 1 and os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        mode = MODES[args.cvf_mode]
+        facts = profile_facts(args.workload, mode) if world == 1 else None
+        h2d = banded.h2d_bytes() if banded is not None else 2 * W * H * 3 * 4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": (f"disparity-sharded x{world}, exchange={args.exchange}") if world > 1 else "single GPU",
-                       "cvf_mode": ["exact", "mixed", "naive"][args.cvf_mode], "variant": args.variant,
-                       "l2": "inputs larger than L2: each step streams 4 x 1.06 GB volumes (raw+filtered, 2 views), no flush needed",
+            "config": {"workload": WORKLOAD,
+                       "parallelism": (f"disparity-sharded x{world}, exchange={args.exchange}") if world > 1 else "single GPU",
+                       "cvf_mode": mode, "variant": args.variant,
+                       "l2": f"inputs larger than L2: each step streams {4 * V * 4 / 1e9:.2f} GB of volumes (raw+filtered, 2 views) per GPU"
+                             + ("" if 4 * V * 4 > 252e6 else "; NOTE: smaller than 2 x L2, L2 reuse between steps is possible"),
                        "stage_ms_last_step": stage},
             "roofline": {"bound": "hbm", "kernel": "cvf_stream_kernel (fused guided filter, both views per launch)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_ms,
-                         "peak_source": peak_src},
-            "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": 2 * W * H * 3 * 4 * (1 if banded else world),
-                    "upload": ("banded: each rank uploads H/N rows, NCCL all-gather over NVLink" if banded else "every rank uploads both images"),
+                         "traffic": (facts or {}).get("dram_bytes_per_launch"),
+                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_ms, "peak_source": peak_src,
+                         "limiter": (facts or {}).get("limiter",
+                                                      "not profiled for this workload/mode; see profiles/ for C4")},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                    "upload": ("banded: each rank uploads H/N rows, NCCL all-gather over NVLink" if banded is not None
+                               else "two-deep pipeline: frame k+1 uploads (copy stream) while frame k computes"),
                     "d2h_bytes_per_step": 2 * W * H * world, "ms_per_step": e2e_ms / args.steps},
             "e2e_u8": {"value": 1e3 / (e2e_u8_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": 2 * W * H * 3 * world,
                        "d2h_bytes_per_step": 2 * W * H * world, "ms_per_step": e2e_u8_ms / args.steps,
-                       "note": "same as e2e but the host frames are 8-bit (psm_set_images_u8)"},
+                       "note": "same as e2e but the host frames are 8-bit (psm_set_images_u8_async)"},
             "gpu_launches": int(launches_per_step * args.steps),
+            "parity_checked": bool(parity and parity["ok"]),
+            "parity": parity,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            threads = min(cores, D)
-            sec, tms = oracle_frame(l, r, threads)
-            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "1 full C4 frame (both views) through the CPU oracle, all host cores",
-                                    "stage_ms": {"cvc": tms[0], "cvf": tms[1], "wta": tms[2]}}
+            cb, _ = cpu_report(l, r, D, WORKLOAD, steps=1, warmup=1)
+            line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     de.close()
     if world > 1:

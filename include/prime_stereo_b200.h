@@ -57,7 +57,12 @@ enum {
     PSM_OPT_CVF_MODE = 1,  /* PSM_CVF_* below; default PSM_CVF_EXACT */
     PSM_OPT_GRAY_MODE = 2, /* 0: fma(c2,.114,fma(c0,.299,c1*.587)) (OpenCV SIMD/IPP builds, default)
                               1: (c0*.299+c1*.587)+c2*.114 (non-FMA OpenCV builds) */
-    PSM_OPT_TIMING = 3     /* 1: record cudaEvents around each stage (default 1) */
+    PSM_OPT_TIMING = 3,    /* 1: record cudaEvents around each stage (default 1) */
+    PSM_OPT_P2P_SYNC = 4   /* fused multi-GPU exchange: 1 (default) = the kernels synchronise across ranks by
+                              device-side flags in the exchange blocks (no library collective, no host barrier);
+                              0 = the caller separates select / reduce / fetch by its own cross-rank barriers */
+    /* keys 100..104 are kernel tuning knobs used by bench.py experiments (variant, rows per segment, extra
+       shared memory, threads per CTA, block remap); they never change results */
 };
 enum {
     PSM_CVF_EXACT = 0, /* streaming fused kernel, every box sum accumulated in fp64: bit-exact q */
@@ -152,9 +157,15 @@ int psm_disp_reduce_keys(psm_ctx* ctx, const uint64_t* d_gathered_left,
  *   psm_disp_reduce_p2p      : this rank reduces its pixel chunk over all ranks' minima and stores the
  *                              winning disparity into EVERY rank's result map;
  *   psm_disp_fetch_p2p       : copy this rank's (complete) result maps to host memory and synchronise.
- * A cross-rank barrier (e.g. a 1-element NCCL all-reduce on the same stream) must separate select from
- * reduce and reduce from fetch.  Every rank owns one exchange block (psm_p2p_create_buffer), shared with
- * the other per-GPU processes through CUDA IPC (psm_ipc_export / psm_ipc_import). */
+ * The three kernels order themselves across ranks through ARRIVE / DONE flag words in the exchange blocks
+ * (release stores over NVLink, acquire loads; PSM_OPT_P2P_SYNC = 1, default): select -> reduce -> fetch can be
+ * enqueued back to back on every rank without any library collective or host barrier, provided every rank runs
+ * the same sequence of frames and each rank's GPU can run its kernels independently of the others (one context
+ * per GPU).  With PSM_OPT_P2P_SYNC = 0 a cross-rank barrier must separate select from reduce and reduce from
+ * fetch.  All launches of one context must stay on ONE stream (psm_set_stream); collectives the caller issues
+ * around them must be ordered against that stream.  Every rank owns one exchange block
+ * (psm_p2p_create_buffer), shared with the other per-GPU processes through CUDA IPC (psm_ipc_export /
+ * psm_ipc_import).  At most 8 ranks. */
 int psm_p2p_create_buffer(psm_ctx* ctx, int nranks, void** d_buffer);
 int psm_ipc_export(psm_ctx* ctx, void* d_ptr, unsigned char handle_out[64]);
 int psm_ipc_import(psm_ctx* ctx, const unsigned char handle[64], void** d_ptr);

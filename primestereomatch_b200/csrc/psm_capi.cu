@@ -42,10 +42,13 @@ struct psm_ctx {
     int up_pending = 0;                     // 0 none, 1 f32 upload pending, 2 u8 upload pending
     uint8_t* dis[2] = {nullptr, nullptr};
     int* guide_flags = nullptr;             // [2] device flags: guide outside the integer-widening domain (see psm_cvf_stream.cuh)
-    unsigned char* p2p_own = nullptr;       // own exchange block: keys [2 views][nranks][chunk] u64 + maps [2 views][H*W] u8
-    unsigned char* p2p_peer[8] = {};        // every rank's exchange block as mapped here
-    void* p2p_imported[8] = {};             // IPC mappings to close at destroy
+    unsigned char* p2p_own = nullptr;       // own exchange block: keys [2 views][nranks][chunk] u64, maps [2 views][H*W] u8, flag words
+    unsigned char* p2p_peer[kMaxRanks] = {};// every rank's exchange block as mapped here
+    void* p2p_imported[kMaxRanks] = {};     // IPC mappings to close at destroy
     int p2p_nimported = 0, p2p_nranks = 0, p2p_rank = 0;
+    unsigned* p2p_counter = nullptr;        // device-local CTA counter of the publishing kernels
+    unsigned p2p_seq = 0;                   // frame sequence number of the device-side exchange flags
+    int p2p_sync = 1;                       // 1: device-side ARRIVE/DONE flags; 0: the caller separates the kernels by its own barriers
     float* alloc[16] = {};                  // raw cudaMalloc pointers behind the halo-offset pointers above
     int nalloc = 0;
     float* ab = nullptr;                    // naive-mode scratch [4][d_count][H][Wp], lazy
@@ -234,11 +237,12 @@ int launch_cvf_stream(psm_ctx* c)
     if (c->cvf_target_rows > 0) target_rows = c->cvf_target_rows;
     plan_segments(c->H, target_rows, &P.nseg, &P.seg_rows);
     // kernel selection: mode (exact / mixed) x tuning variant (PSM option 100)
-    //   variant 0 (shipped): integer widening + history ring in tensor memory
+    //   variant 0 (shipped): integer widening + history ring in tensor memory (+ L1 prefetch of the next guide rows in exact mode)
     //   variant 1: F2F conversions, ring in shared memory (the round-1 kernel, kept as the A/B baseline; exact only)
     //   variant 2: integer widening, ring in shared memory
     //   variant 3: F2F conversions, ring in tensor memory (exact only)
     //   variant 4: as 0 with <= 128 registers (4 CTAs of 128 threads per SM)
+    //   variants 5-8: experiments recorded in DESIGN.md section 9 (prefetch on/off, stage-2 F2F, 144/152-register builds)
     using kern_t = void (*)(CvfParams);
     kern_t kern = nullptr;
     bool tm = true;
@@ -248,6 +252,8 @@ int launch_cvf_stream(psm_ctx* c)
         case 4: kern = cvf_stream_kernel<4, 1, kS2Mixed, 1>; break;
         case 5: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1, 1>; break;
         case 6: kern = cvf_stream_kernel<4, 1, kS2Mixed, 1, 1>; break;
+        case 7: kern = cvf_stream_kernel<5, 1, kS2Mixed, 1, 0>; break;   // 144 registers
+        case 8: kern = cvf_stream_kernel<6, 1, kS2Mixed, 1, 0>; break;   // 152 registers
         default: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1>; break;
         }
     } else {
@@ -256,10 +262,10 @@ int launch_cvf_stream(psm_ctx* c)
         case 2: kern = cvf_stream_kernel<3, 1, kS2Exact, 0>; tm = false; break;
         case 3: kern = cvf_stream_kernel<3, 0, kS2Exact, 1>; break;
         case 4: kern = cvf_stream_kernel<4, 1, kS2Exact, 1>; break;
-        case 5: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 1>; break;
         case 6: kern = cvf_stream_kernel<3, 2, kS2Exact, 1, 0>; break;
         case 7: kern = cvf_stream_kernel<3, 2, kS2Exact, 1, 1>; break;
-        default: kern = cvf_stream_kernel<3, 1, kS2Exact, 1>; break;
+        case 8: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 0>; break;
+        default: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 1>; break;
         }
     }
     const size_t smem = (tm ? 0 : (size_t)8 * 4 * nthreads * sizeof(float4)) + (size_t)c->cvf_extra_smem;
@@ -380,6 +386,7 @@ int psm_destroy(psm_ctx* c)
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     for (int i = 0; i < c->p2p_nimported; ++i) cudaIpcCloseMemHandle(c->p2p_imported[i]);
     cudaFree(c->p2p_own);
+    cudaFree(c->p2p_counter);
     for (int i = 0; i < c->nalloc; ++i) cudaFree(c->alloc[i]);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     for (int v = 0; v < 2; ++v) { cudaFree(c->stage_in[v]); cudaFree(c->stage_alt[v]); cudaFree(c->dis[v]); }
@@ -414,14 +421,17 @@ int psm_set_option(psm_ctx* c, int key, int value)
     case PSM_OPT_TIMING:
         c->timing = value ? 1 : 0;
         return PSM_OK;
-    case 100:  // undocumented: streaming-kernel variant selector for tuning experiments
+    case PSM_OPT_P2P_SYNC:
+        c->p2p_sync = value ? 1 : 0;
+        return PSM_OK;
+    case 100:  // streaming-kernel variant selector for tuning experiments
         c->cvf_variant = value;
         return PSM_OK;
     case 104:  // undocumented: block->work remap so that co-resident CTAs are work neighbours (0/1)
         c->cvf_remap = value;
         return PSM_OK;
     case 103:  // undocumented: threads per CTA of the streaming kernel (64 / 96 / 128)
-        if (value != 0 && (value % 32 != 0 || value < 32 || value > 128)) return fail(c, PSM_EINVAL, "bad thread count");
+        if (value != 0 && (value % 32 != 0 || value < 32 || value > kCvfMaxThreads)) return fail(c, PSM_EINVAL, "bad thread count");
         c->cvf_threads = value;
         return PSM_OK;
     case 102:  // undocumented: extra dynamic shared memory per CTA (bytes) to throttle occupancy in experiments
@@ -626,20 +636,27 @@ int psm_disp_reduce_keys(psm_ctx* c, const uint64_t* d_gathered_left, const uint
     return PSM_OK;
 }
 
-// Exchange block of one rank: [2 views][nranks][chunk] uint64 keys, then [2 views][H*W] u8 result maps.
+// Exchange block of one rank: [2 views][nranks][chunk] uint64 keys, [2 views][H*W] u8 result maps,
+// [2 views][2 * kMaxRanks] u32 flag words (ARRIVE per rank, DONE per rank), each part 256-byte aligned.
 static size_t p2p_chunk(const psm_ctx* c, int nranks) { return ((size_t)c->W * c->H + nranks - 1) / nranks; }
 static size_t p2p_keys_bytes(const psm_ctx* c, int nranks) { return (size_t)2 * nranks * p2p_chunk(c, nranks) * sizeof(unsigned long long); }
+static size_t p2p_maps_bytes(const psm_ctx* c) { return (((size_t)2 * c->W * c->H) + 255) & ~(size_t)255; }
+static size_t p2p_flags_bytes() { return (size_t)2 * 2 * kMaxRanks * sizeof(unsigned); }
 
 int psm_p2p_create_buffer(psm_ctx* c, int nranks, void** d_buffer)
 {
     if (int rc = bind(c)) return rc;
-    if (nranks < 1 || nranks > 8 || !d_buffer) return fail(c, PSM_EINVAL, "bad nranks %d (1..8)", nranks);
+    if (nranks < 1 || nranks > kMaxRanks || !d_buffer) return fail(c, PSM_EINVAL, "bad nranks %d (1..%d)", nranks, kMaxRanks);
     if (c->p2p_own) { cudaFree(c->p2p_own); c->p2p_own = nullptr; }
-    const size_t bytes = p2p_keys_bytes(c, nranks) + (size_t)2 * c->W * c->H;
-    PSM_CUDA(c, cudaMalloc(&c->p2p_own, bytes));
-    PSM_CUDA(c, cudaMemsetAsync(c->p2p_own, 0xff, bytes, c->stream));
+    const size_t kb = p2p_keys_bytes(c, nranks), mb = p2p_maps_bytes(c), fb = p2p_flags_bytes();
+    PSM_CUDA(c, cudaMalloc(&c->p2p_own, kb + mb + fb));
+    PSM_CUDA(c, cudaMemsetAsync(c->p2p_own, 0xff, kb + mb, c->stream));
+    PSM_CUDA(c, cudaMemsetAsync(c->p2p_own + kb + mb, 0, fb, c->stream));
+    if (!c->p2p_counter) PSM_CUDA(c, cudaMalloc(&c->p2p_counter, sizeof(unsigned)));
+    PSM_CUDA(c, cudaMemsetAsync(c->p2p_counter, 0, sizeof(unsigned), c->stream));
     PSM_CUDA(c, cudaStreamSynchronize(c->stream));
     c->p2p_nranks = nranks;
+    c->p2p_seq = 0;
     *d_buffer = c->p2p_own;
     return PSM_OK;
 }
@@ -657,7 +674,7 @@ int psm_ipc_export(psm_ctx* c, void* d_ptr, unsigned char handle_out[64])
 int psm_ipc_import(psm_ctx* c, const unsigned char handle[64], void** d_ptr)
 {
     if (int rc = bind(c)) return rc;
-    if (c->p2p_nimported >= 8) return fail(c, PSM_EINVAL, "too many imported buffers");
+    if (c->p2p_nimported >= kMaxRanks) return fail(c, PSM_EINVAL, "too many imported buffers");
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
     PSM_CUDA(c, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
@@ -681,11 +698,15 @@ static void p2p_fill(const psm_ctx* c, int view, P2pPeers& peers)
 {
     const size_t chunk = p2p_chunk(c, c->p2p_nranks);
     const size_t npix = (size_t)c->W * c->H;
+    const size_t kb = p2p_keys_bytes(c, c->p2p_nranks), mb = p2p_maps_bytes(c);
     peers.nranks = c->p2p_nranks; peers.rank = c->p2p_rank; peers.chunk = (unsigned)chunk;
-    for (int r = 0; r < 8; ++r) {
+    peers.counter = c->p2p_counter;
+    peers.seq = c->p2p_sync ? c->p2p_seq : 0u;
+    for (int r = 0; r < kMaxRanks; ++r) {
         unsigned char* base = r < c->p2p_nranks ? c->p2p_peer[r] : nullptr;
         peers.keys[r] = base ? reinterpret_cast<unsigned long long*>(base) + (size_t)view * c->p2p_nranks * chunk : nullptr;
-        peers.maps[r] = base ? base + p2p_keys_bytes(c, c->p2p_nranks) + (size_t)view * npix : nullptr;
+        peers.maps[r] = base ? base + kb + (size_t)view * npix : nullptr;
+        peers.flags[r] = base ? reinterpret_cast<unsigned*>(base + kb + mb) + (size_t)view * 2 * kMaxRanks : nullptr;
     }
 }
 
@@ -695,6 +716,7 @@ int psm_disp_select_keys_p2p(psm_ctx* c)
     if (!c->p2p_own || !c->p2p_peer[0]) return fail(c, PSM_ESTATE, "psm_p2p_create_buffer / psm_p2p_set_peers first");
     if (!c->filtered) return fail(c, PSM_ESTATE, "psm_disp_select_keys_p2p before psm_cost_filter");
     if (int rc = stage_begin(c, 3)) return rc;
+    c->p2p_seq++;   // one sequence number per frame, identical on every rank (all ranks run the same frames)
     for (int v = 0; v < 2; ++v) {
         P2pPeers peers;
         p2p_fill(c, v, peers);
@@ -715,6 +737,14 @@ int psm_disp_reduce_p2p(psm_ctx* c)
         p2p_fill(c, v, peers);
         chunk_reduce_kernel<<<(peers.chunk + 255) / 256, 256, 0, c->stream>>>(peers, npix);
         PSM_LAUNCH_CHECK(c);
+    }
+    if (c->p2p_sync) {  // local maps complete + every reducer done with this rank's keys
+        for (int v = 0; v < 2; ++v) {
+            P2pPeers peers;
+            p2p_fill(c, v, peers);
+            p2p_wait_done_kernel<<<1, 32, 0, c->stream>>>(peers.flags[c->p2p_rank], c->p2p_nranks, c->p2p_seq);
+            PSM_LAUNCH_CHECK(c);
+        }
     }
     return PSM_OK;
 }

@@ -73,7 +73,7 @@ namespace psm {
 constexpr int kStripOut = 112;  // output columns per warp
 constexpr int kStripIn = 128;   // input columns per warp
 constexpr int kCvfThreads = 96;       // default CTA size: 3 slice-warps, 48 KB ring, 4 CTAs/SM
-constexpr int kCvfMaxThreads = 128;   // upper bound the register allocation is sized for
+constexpr int kCvfMaxThreads = 512;   // 16 warps: every ring of an SM's tensor memory in one CTA
 
 // stage-2 modes (template parameter S2M)
 constexpr int kS2Exact = 0;  // fp64 running sums
@@ -192,7 +192,7 @@ __device__ __forceinline__ void tmem_st16(unsigned taddr, const f2x2 (&v)[4])
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-constexpr unsigned kTmemCols = 128;   // columns per CTA: one 128-column ring per lane quarter (warp)
+constexpr unsigned kTmemCols = 128;   // one ring = 128 columns of one lane quarter; a CTA allocates one block per 4 warps
 
 // MINB: resident CTAs per SM the register allocation is sized for (3 -> <=168 regs, 4 -> <=128);
 // IW  : 0 = F2F everywhere; 1 = integer widening into the scaled domain in both stages; 2 = integer widening in
@@ -200,8 +200,12 @@ constexpr unsigned kTmemCols = 128;   // columns per CTA: one 128-column ring pe
 // S2M : kS2Exact / kS2Mixed
 // TM  : 1 = history ring in tensor memory (tcgen05.ld/st), 0 = in shared memory
 // PF  : 1 = prefetch the next step's guide rows into L1
+// register budgets by MINB: 3 -> 168 regs (3 CTAs x 128 thr or 4 x 96: 12 warps/SM); 4 -> 128 regs (16 warps);
+// 5 -> 144 regs (2 CTAs x 224 thr = 14 warps, two TMEM column blocks per lane quarter); 6 -> 152 regs (13 warps)
+constexpr int cvf_max_regs(int minb) { return minb == 3 ? 168 : (minb == 4 ? 128 : (minb == 5 ? 144 : 152)); }
+
 template <int MINB, int IW, int S2M, int TM, int PF = 0>
-__global__ void __launch_bounds__(kCvfMaxThreads, MINB)
+__global__ void __maxnreg__(cvf_max_regs(MINB))
 cvf_stream_kernel(const CvfParams P)
 {
     extern __shared__ float4 ring[];  // TM == 0: [8 slots][4 planes][blockDim.x threads]
@@ -230,19 +234,22 @@ cvf_stream_kernel(const CvfParams P)
     const int dlc_raw = dgroup * wpc + warp;
     const bool active = dlc_raw < P.Dloc;
     const int dlc = active ? dlc_raw : P.Dloc - 1;
-    unsigned tring = 0;   // TMEM address of this warp's ring (lane quarter = warp % 4, column 0 of the CTA's allocation)
+    unsigned tring = 0;   // TMEM address of this warp's ring (lane quarter = warp % 4, column block = warp / 4)
+    // columns this CTA allocates: one 128-column block per group of 4 warps, rounded up to a power of two
+    const unsigned tmem_cols = wpc <= 4 ? kTmemCols : (wpc <= 8 ? 2 * kTmemCols : 4 * kTmemCols);
     if (TM) {
         // one warp allocates the CTA's columns, everybody reads the base after a fenced barrier; this
         // barrier and the one before the deallocation are the only CTA-wide synchronisations
         if (warp == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                         :: "r"((unsigned)__cvta_generic_to_shared(&tmem_base_smem)), "r"(kTmemCols) : "memory");
+                         :: "r"((unsigned)__cvta_generic_to_shared(&tmem_base_smem)), "r"(tmem_cols) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tring = tmem_base_smem + ((unsigned)(warp & 3) << 21);   // lane field = bits 31..16: (warp%4)*32 << 16
+        // lane field = bits 31..16: (warp%4)*32 << 16; warps 4.. use the next 128-column block of their lane quarter
+        tring = tmem_base_smem + ((unsigned)(warp & 3) << 21) + (unsigned)(warp >> 2) * kTmemCols;
     } else if (!active) {
         return;  // warps never synchronise with each other
     }
@@ -636,7 +643,7 @@ cvf_stream_kernel(const CvfParams P)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (warp == 0)
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_smem), "r"(kTmemCols) : "memory");
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_smem), "r"(tmem_cols) : "memory");
     }
 }
 

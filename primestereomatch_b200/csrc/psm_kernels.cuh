@@ -483,15 +483,52 @@ __global__ void __launch_bounds__(256) wta_kernel(const float* __restrict__ vol,
 //   wta_scatter_kernel : the WTA scan of wta_kernel, then the packed (cost,d) minimum of every pixel
 //                        is stored into its reducer's exchange block, slot [this rank][pixel-in-chunk]
 //                        (peer device memory, plain st.global over NVLink) -- compute + scatter in one kernel;
-//   chunk_reduce_kernel: the reducer takes the min over the nranks slots of its chunk and stores the
-//                        winning disparity (u8) into EVERY rank's result map -- reduce + gather in one kernel.
-// A cross-rank barrier separates the two kernels and follows the second one.
+//                        its last CTA then raises this rank's ARRIVE flag in every peer's block;
+//   chunk_reduce_kernel: waits for the ARRIVE flags of all ranks (acquire loads on its own block), takes
+//                        the min over the nranks slots of its chunk, stores the winning disparity (u8)
+//                        into EVERY rank's result map -- reduce + gather in one kernel -- and its last CTA
+//                        raises this rank's DONE flag in every peer's block;
+//   p2p_wait_done_kernel: one thread spins until all ranks' DONE flags carry this frame's sequence number;
+//                        after it the local result maps are complete and the key slots may be overwritten.
+// Flags are monotonically increasing frame sequence numbers (never reset), written with release and read
+// with acquire semantics at system scope, so the exchange needs NO library collective or host barrier:
+// a waiting kernel only ever waits for kernels of other GPUs that do not wait for it.
+constexpr int kMaxRanks = 8;
+
 struct P2pPeers {
-    unsigned long long* keys[8];  // per rank: exchange block of this view  [nranks][chunk]
-    unsigned char* maps[8];       // per rank: result map of this view       [H*W]
+    unsigned long long* keys[kMaxRanks];  // per rank: exchange block of this view  [nranks][chunk]
+    unsigned char* maps[kMaxRanks];       // per rank: result map of this view       [H*W]
+    unsigned* flags[kMaxRanks];           // per rank: flag words of this view: arrive[kMaxRanks], done[kMaxRanks]
+    unsigned* counter;                    // device-local CTA counter of the launching rank (zero between launches)
     int nranks, rank;
-    unsigned chunk;               // pixels per chunk (last chunk may be partly unused)
+    unsigned chunk;                       // pixels per chunk (last chunk may be partly unused)
+    unsigned seq;                         // frame sequence number (>= 1)
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// called by every thread of the CTA after its peer stores: the LAST CTA of the launch publishes `seq` in slot
+// flag_base[rank] of every peer's flag words
+__device__ __forceinline__ void p2p_publish(const P2pPeers& peers, int flag_offset)
+{
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence_system();                       // this CTA's peer stores are visible system-wide ...
+        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned prev = atomicAdd(peers.counter, 1u);
+        if (prev == total - 1) {                      // ... before the last CTA (which observed every increment) raises the flags
+            __threadfence();
+            *peers.counter = 0;
+            for (int r = 0; r < peers.nranks; ++r) st_release_sys(peers.flags[r] + flag_offset + peers.rank, peers.seq);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256) wta_scatter_kernel(const float* __restrict__ vol, int W, int H, int Wp, int d_begin, int d_count,
                                                           P2pPeers peers)
@@ -533,21 +570,39 @@ __global__ void __launch_bounds__(256) wta_scatter_kernel(const float* __restric
             peers.keys[owner][(size_t)peers.rank * peers.chunk + (pix - owner * peers.chunk)] = stage[warp][idx];  // peer (or own) memory
         }
     }
+    if (peers.seq) p2p_publish(peers, 0);   // ARRIVE
 }
 
 __global__ void __launch_bounds__(256) chunk_reduce_kernel(P2pPeers peers, unsigned npix)
 {
+    if (peers.seq) {   // wait until every rank's minima for this frame have landed in this rank's block
+        if (threadIdx.x < (unsigned)peers.nranks) {
+            const unsigned* f = peers.flags[peers.rank] + threadIdx.x;
+            while ((int)(ld_acquire_sys(f) - peers.seq) < 0) __nanosleep(64);
+        }
+        __syncthreads();
+    }
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;   // pixel inside this rank's chunk
     const unsigned pix = (unsigned)peers.rank * peers.chunk + i;
-    if (i >= peers.chunk || pix >= npix) return;
-    const unsigned long long* mine = peers.keys[peers.rank];
-    unsigned long long k = mine[i];
-    for (int r = 1; r < peers.nranks; ++r) {
-        const unsigned long long v = mine[(size_t)r * peers.chunk + i];
-        k = v < k ? v : k;
+    if (i < peers.chunk && pix < npix) {
+        const unsigned long long* mine = peers.keys[peers.rank];
+        unsigned long long k = __ldcg(mine + i);   // L2: the slots were written by peer GPUs
+        for (int r = 1; r < peers.nranks; ++r) {
+            const unsigned long long v = __ldcg(mine + (size_t)r * peers.chunk + i);
+            k = v < k ? v : k;
+        }
+        const unsigned char d = (unsigned char)(k & 0xffu);
+        for (int r = 0; r < peers.nranks; ++r) peers.maps[r][pix] = d;  // every rank receives the final map
     }
-    const unsigned char d = (unsigned char)(k & 0xffu);
-    for (int r = 0; r < peers.nranks; ++r) peers.maps[r][pix] = d;  // every rank receives the final map
+    if (peers.seq) p2p_publish(peers, kMaxRanks);   // DONE
+}
+
+__global__ void p2p_wait_done_kernel(const unsigned* flags /* this rank's flag words of one view */, int nranks, unsigned seq)
+{
+    if (threadIdx.x < (unsigned)nranks) {
+        const unsigned* f = flags + kMaxRanks + threadIdx.x;
+        while ((int)(ld_acquire_sys(f) - seq) < 0) __nanosleep(64);
+    }
 }
 
 // Final step of the sharded WTA: min over ranks of the packed keys, low 8 bits -> u8 map.

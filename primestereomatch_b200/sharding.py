@@ -1,8 +1,11 @@
-"""Host-side logic of the disparity-sharded (multi-GPU) path: which global disparity slices a
-rank owns, and the one exchange step (all-gather of packed per-pixel minima).
+"""Host-side logic of the disparity-sharded (multi-GPU) path: which global disparity slices a rank
+owns, the one exchange step of the path (per-pixel packed minima -> final maps) and the banded image
+upload that keeps the per-rank PCIe traffic constant as ranks are added.
 
-One process per GPU; `torch.distributed` supplies the collective (NCCL on GPUs, gloo in the CPU
-tests).  Device work stays in the C-ABI: psm_disp_select_keys / psm_disp_reduce_keys.
+One process per GPU; `torch.distributed` supplies rendezvous and the library collectives (NCCL on
+GPUs, gloo in the CPU tests).  Device work stays in the C-ABI (include/prime_stereo_b200.h).
+Reference counterpart: the reference shards nothing (single process); its unit of parallel work is the
+disparity slice (src/DispEst.cpp:235-268), which is what is sharded here.
 """
 import ctypes as C
 
@@ -20,12 +23,29 @@ def shard_range(max_disp, world, rank):
     return d_begin, d_count
 
 
+def band_rows(height, world, rank):
+    """Row band [r0, r1) of the images that rank `rank` uploads; bands are equal-sized (the last may be short)."""
+    rows = (height + world - 1) // world
+    return min(height, rank * rows), min(height, (rank + 1) * rows), rows
+
+
+def bind_to_current_stream(de):
+    """Run every launch of `de` on torch's CURRENT stream, so that collectives torch issues (which are ordered
+    on that stream) are ordered against the context's kernels.  The legacy default stream (handle 0) is passed
+    as cudaStreamLegacy (0x1) because a NULL handle means 'the context's own stream' to psm_set_stream."""
+    import torch
+    h = torch.cuda.current_stream().cuda_stream
+    capi.check(capi.lib().psm_set_stream(de.handle, C.c_void_p(h if h else 1)), de.handle)
+
+
 def gather_and_reduce(de, keys, gathered, world, lmap=None, rmap=None, group=None):
-    """keys: int64 CUDA tensor [2, H*W] (this rank's packed minima, written by
-    psm_disp_select_keys); gathered: int64 CUDA tensor [2, world, H*W].  Runs the single
-    all-gather per view and the final min -> u8 maps (optionally copied to host arrays)."""
+    """Library baseline of the exchange.  keys: int64 CUDA tensor [2, H*W] (this rank's packed minima, written by
+    psm_disp_select_keys); gathered: int64 CUDA tensor [2, world, H*W].  One all-gather per view, then the final
+    min -> u8 maps (optionally copied to host arrays).  The context is bound to torch's current stream first:
+    the all-gathers must not overtake the select kernels."""
     import torch.distributed as dist
     L = capi.lib()
+    bind_to_current_stream(de)
     capi.check(L.psm_disp_select_keys(de.handle, keys[0].data_ptr(), keys[1].data_ptr()), de.handle)
     dist.all_gather_into_tensor(gathered[0].view(-1), keys[0], group=group)
     dist.all_gather_into_tensor(gathered[1].view(-1), keys[1], group=group)
@@ -37,16 +57,20 @@ def gather_and_reduce(de, keys, gathered, world, lmap=None, rmap=None, group=Non
 
 class P2PExchange:
     """Sharded WTA fused with its exchange over NVLink peer memory (see include/prime_stereo_b200.h):
-    select() = WTA + scatter of packed minima into the reducers' blocks, reduce() = chunk min +
-    gather of the u8 result into every rank's map, fetch() = D2H.  barrier() (a 1-element NCCL
-    all-reduce on the current stream) must run between select/reduce and reduce/fetch.
-    Exchange blocks are shared between the per-GPU processes through CUDA IPC handles exchanged once."""
+    select() = WTA + scatter of packed minima into the reducers' blocks, reduce() = chunk min + gather of the u8
+    result into every rank's map, fetch() = D2H.  The kernels order themselves across ranks with device-side
+    ARRIVE / DONE flags in the exchange blocks: a frame needs no collective and no host barrier.
+    Exchange blocks are shared between the per-GPU processes through CUDA IPC handles exchanged once.
+    device_sync=False falls back to caller-side barriers (a 1-element all-reduce on the context's stream)."""
 
-    def __init__(self, de, world, rank, group=None):
+    def __init__(self, de, world, rank, group=None, device_sync=True):
         import torch
         import torch.distributed as dist
         self.de, self.world, self.rank, self.group = de, world, rank, group
+        self.device_sync = bool(device_sync)
         L = capi.lib()
+        bind_to_current_stream(de)   # the setup collectives below and (without device_sync) the barriers share its stream
+        capi.check(L.psm_set_option(de.handle, capi.PSM_OPT_P2P_SYNC, int(self.device_sync)), de.handle)
         own = C.c_void_p()
         capi.check(L.psm_p2p_create_buffer(de.handle, world, C.byref(own)), de.handle)
         handle = C.create_string_buffer(64)
@@ -65,14 +89,14 @@ class P2PExchange:
                 ptrs[r] = p.value
         capi.check(L.psm_p2p_set_peers(de.handle, ptrs, world, rank), de.handle)
         self._flag = torch.zeros(1, device="cuda")
-        dist.barrier(group=group)
+        dist.barrier(group=group)   # every rank's block is mapped and zeroed before the first frame
 
     def select(self):
         capi.check(capi.lib().psm_disp_select_keys_p2p(self.de.handle), self.de.handle)
 
     def barrier(self):
         import torch.distributed as dist
-        dist.all_reduce(self._flag, group=self.group)  # stream-ordered cross-rank barrier
+        dist.all_reduce(self._flag, group=self.group)  # stream-ordered cross-rank barrier (device_sync=False only)
 
     def reduce(self):
         capi.check(capi.lib().psm_disp_reduce_p2p(self.de.handle), self.de.handle)
@@ -82,7 +106,43 @@ class P2PExchange:
                    self.de.handle)
 
     def frame(self, lmap_ptr=None, rmap_ptr=None):
-        """select -> barrier -> reduce -> barrier [-> fetch]"""
-        self.select(); self.barrier(); self.reduce(); self.barrier()
+        """select -> reduce [-> fetch]; with device_sync=False a barrier follows select and reduce."""
+        self.select()
+        if not self.device_sync:
+            self.barrier()
+        self.reduce()
+        if not self.device_sync:
+            self.barrier()
         if lmap_ptr is not None:
             self.fetch(lmap_ptr, rmap_ptr)
+
+
+class BandedUpload:
+    """N > 1, frames in HOST memory: every rank uploads only its row band of both images over PCIe (H/N rows) and
+    the bands are all-gathered over NVLink, so the host->device bytes per rank shrink with N instead of every
+    rank uploading both full images.  The gathered interleaved images feed psm_set_images_device."""
+
+    def __init__(self, de, world, rank, dtype="float32", group=None):
+        import torch
+        self.de, self.world, self.rank, self.group = de, world, rank, group
+        self.r0, self.r1, self.rows = band_rows(de.hei, world, rank)
+        tdt = torch.float32 if dtype == "float32" else torch.uint8
+        if tdt is not torch.float32:
+            raise ValueError("BandedUpload gathers float32 frames (psm_set_images_device takes float images)")
+        W = de.wid
+        self.band = [torch.zeros((self.rows, W, 3), dtype=tdt, device="cuda") for _ in range(2)]
+        self.full = [torch.empty((world * self.rows, W, 3), dtype=tdt, device="cuda") for _ in range(2)]
+        self.step_bytes = W * 3 * 4
+        bind_to_current_stream(de)   # the all-gathers and the ingest kernels share one stream
+
+    def h2d_bytes(self):
+        return 2 * (self.r1 - self.r0) * self.de.wid * 3 * 4
+
+    def upload(self, left_pinned, right_pinned):
+        """left_pinned / right_pinned: pinned host tensors [H, W, 3] float32 of the FULL frame (each rank reads its band)."""
+        import torch.distributed as dist
+        for k, src in enumerate((left_pinned, right_pinned)):
+            self.band[k][: self.r1 - self.r0].copy_(src[self.r0:self.r1], non_blocking=True)
+            dist.all_gather_into_tensor(self.full[k].view(-1), self.band[k].view(-1), group=self.group)
+        capi.check(capi.lib().psm_set_images_device(self.de.handle, self.full[0].data_ptr(), self.step_bytes,
+                                                    self.full[1].data_ptr(), self.step_bytes), self.de.handle)
