@@ -18,6 +18,8 @@
  *   psm_cost_filter       <-> DispEst::CostFilter_GPU            src/DispEst.cpp:299-308
  *   psm_disp_select       <-> DispEst::DispSelect_GPU + D2H in DispSel_cl::CVSelect
  *                                                                 src/DispEst.cpp:323-328, src/DispSel_cl.cpp:123-134
+ *   psm_post_process      <-> DispEst::PostProcess_GPU -> PP::processDM -> JointWMF::filter
+ *                                                                 src/DispEst.cpp:338-344, src/PP.cpp:402-425
  *   psm_read_cost_slice   <-> DispEst::printCV (cost-slice dump) src/DispEst.cpp:181-194
  *   psm_stage_ms          <-> cvc_time/cvf_time/dispsel_time     src/StereoMatch.cpp:209-241
  *
@@ -138,6 +140,18 @@ int psm_disp_select_async(psm_ctx* ctx, uint8_t* left, size_t left_step,
 /* Stage 3 without the D2H copy: maps stay on the device (see psm_device_ptr). Asynchronous. */
 int psm_disp_select_device(psm_ctx* ctx);
 
+/* Stage 4: post-processing of both maps -- the joint weighted-median filter of PP::processDM (window 19x19,
+ * "exp" colour weights on the 6-bit-quantised left / right image, JointWMF defaults), on the device; the
+ * reference runs this stage on the CPU even in GPU mode (src/DispEst.cpp:338-344).  Input: the maps of the last
+ * selection stage (for a sharded context with the fused exchange: the complete maps of psm_disp_reduce_p2p);
+ * output: filtered u8 maps copied to HOST memory (row steps in bytes), synchronises.
+ * Parity: equals the reference's JointWMF whenever the feature image has <= 256 distinct 6-bit colours; beyond
+ * that the reference clusters colours with an RNG-seeded cv::kmeans (an approximation by its own documentation,
+ * JointWMF.h:70-72) while this stage evaluates the un-clustered weights -- see DESIGN.md. */
+int psm_post_process(psm_ctx* ctx, uint8_t* left, size_t left_step, uint8_t* right, size_t right_step);
+/* Same without the D2H copy (maps stay on the device: psm_device_ptr selectors 4, 5). Asynchronous. */
+int psm_post_process_device(psm_ctx* ctx);
+
 /* Sharded stage 3a: per-pixel packed minima over this context's slices, written to DEVICE
  * buffers of H*W uint64 each:  key = (order_preserving_u32(cost) << 32) | global_d.
  * min() over ranks' keys reproduces the reference's strict-< / lowest-d tie-break. Asynchronous. */
@@ -185,11 +199,11 @@ int psm_read_guide_plane(psm_ctx* ctx, int view, int plane, float* dst, size_t d
 int psm_read_ab_slice(psm_ctx* ctx, int view, int d, float* a3, float* b);
 
 /* Device pointers for zero-copy callers / benchmarks. what: 0 left volume, 1 right volume,
- * 2 left u8 map, 3 right u8 map.  pitch_elems receives the row pitch in elements. */
+ * 2 left u8 map, 3 right u8 map, 4 / 5 post-processed left / right u8 map.  pitch_elems receives the row pitch in elements. */
 int psm_device_ptr(psm_ctx* ctx, int what, void** ptr, size_t* pitch_elems);
 
 /* Last measured stage durations in milliseconds (cudaEvent pairs on the context stream):
- * stage 0 ingest (H2D + planar/gradient), 1 CVC, 2 CVF (guide + filter), 3 WTA, 4 CVF filter kernel only.
+ * stage 0 ingest (H2D + planar/gradient), 1 CVC, 2 CVF (guide + filter), 3 WTA, 4 CVF filter kernel only, 5 post-process.
  * Synchronises on the stage's end event. */
 int psm_stage_ms(psm_ctx* ctx, int stage, float* ms);
 

@@ -47,6 +47,8 @@ def lib():
         L.orc_disp_select.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _u8p, _u8p]
         L.orc_pipeline.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    _f32p, _f32p, _u8p, _u8p, _f64p]
+        L.orc_wmf.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, _u8p]
+        L.orc_f32_to_u8x255.argtypes = [_f32p, _u8p, C.c_size_t]
         for name in ("orc_cost_const", "orc_cost_filter", "orc_disp_select", "orc_pipeline"):
             getattr(L, name).restype = C.c_int
         _LIB = L
@@ -175,4 +177,16 @@ def pipeline(l, r, D, threads=8, gray_mode=0, keep_volumes=False):
     out = {"lDis": ld, "rDis": rd, "times_ms": t.tolist()}
     if keep_volumes:
         out["lVol"], out["rVol"] = lv, rv
+    return out
+
+
+def post_process(img3_f32, disp, r=9):
+    """PP::processDM's live code for one view (src/PP.cpp:414-422), un-clustered restatement (see stereo_oracle.c)."""
+    img3 = _c(img3_f32)
+    disp = _c(disp, np.uint8)
+    H, W = disp.shape
+    img8 = np.empty(img3.shape, np.uint8)
+    lib().orc_f32_to_u8x255(img3.reshape(-1), img8.reshape(-1), img3.size)
+    out = np.empty((H, W), np.uint8)
+    lib().orc_wmf(disp, img8, W, H, r, out)
     return out

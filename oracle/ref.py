@@ -36,6 +36,7 @@ def lib():
         L.ref_guided_filter.argtypes = [_f32p, C.c_int, C.c_int, _f32p, _f32p]
         L.ref_wta.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
         L.ref_buildcv.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
+        L.ref_post_process.argtypes = [_f32p, _u8p, C.c_int, C.c_int, C.c_int, _u8p, C.POINTER(C.c_int)]
         L.ref_build_info.restype = C.c_char_p
         _LIB = L
     return _LIB
@@ -87,3 +88,15 @@ def buildcv(l, r, d, right=False, gray_mode=0):
     out = np.empty((H, W), np.float32)
     lib().ref_buildcv(l, r, W, H, d, int(right), gray_mode, out)
     return out
+
+
+def post_process(img3, disp, r=9):
+    """One view of PP::processDM's live code (src/PP.cpp:414-422) through the reference's own JointWMF.h.
+    -> (filtered u8 map, number of distinct 6-bit colours of the feature image).  The clustering inside is the
+    reference's only when that number is <= 256 (oracle/shim kmeans stand-in)."""
+    img3, disp = _c(img3), _c(disp, np.uint8)
+    H, W = disp.shape
+    out = np.empty((H, W), np.uint8)
+    n = C.c_int(0)
+    lib().ref_post_process(img3, disp, W, H, r, out, C.byref(n))
+    return out, n.value

@@ -11,6 +11,7 @@
 #include "CVC.h"
 #include "CVF.h"
 #include "DispSel.h"
+#include "JointWMF.h"   // vendored CUHK weighted-median filter, compiled unmodified from /root/reference/include
 
 #include <vector>
 
@@ -171,6 +172,34 @@ int ref_buildcv(const float* l, const float* r, int W, int H, int d, int right, 
     if (right) constructor.buildCV_right(rImg, lImg, rGrdX, lGrdX, d, c);   // DispEst.cpp:217
     else constructor.buildCV_left(lImg, rImg, lGrdX, rGrdX, d, c);
     copy_out(c, cost, W, H);
+    return 0;
+}
+
+// One view of PP::processDM's live code (src/PP.cpp:414-422): img.convertTo(CV_8UC3, 255) then
+// JointWMF::filter(disp, img8UC3, MED_SZ/2 = 9) with its defaults (sigma 25.5, nI = nF = 256, "exp" weights).
+// The feature clustering inside (JointWMF.h:586-591) calls cv::kmeans, which the shim can only stand in for
+// (see shim/opencv2/opencv.hpp): the result is the reference's only when the image has <= 256 distinct 6-bit colours.
+int ref_post_process(const float* img, const unsigned char* disp, int W, int H, int r, unsigned char* out, int* n_colours)
+{
+    Mat Img(H, W, CV_32FC3, (void*)img);
+    Mat Img8;
+    Img.convertTo(Img8, CV_8UC3, 255);
+    if (n_colours) {   // distinct 6-bit colours (what JointWMF.h:552-568 counts)
+        std::vector<unsigned char> seen(64 * 64 * 64, 0);
+        int cnt = 0;
+        for (int y = 0; y < H; ++y) {
+            const unsigned char* p = Img8.ptr<unsigned char>(y);
+            for (int x = 0; x < W; ++x) {
+                const int k = ((p[3 * x] >> 2) * 64 + (p[3 * x + 1] >> 2)) * 64 + (p[3 * x + 2] >> 2);
+                if (!seen[k]) { seen[k] = 1; ++cnt; }
+            }
+        }
+        *n_colours = cnt;
+    }
+    Mat D = Mat::zeros(H, W, CV_8UC1);
+    for (int y = 0; y < H; ++y) memcpy(D.ptr<unsigned char>(y), disp + (size_t)y * W, W);
+    Mat res = JointWMF::filter(D, Img8, r);
+    for (int y = 0; y < H; ++y) memcpy(out + (size_t)y * W, res.ptr<unsigned char>(y), W);
     return 0;
 }
 

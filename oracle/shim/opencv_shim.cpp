@@ -3,6 +3,7 @@
 // oracle/stereo_oracle.c, which is pinned against python cv2 (tests/test_oracle.py).
 #include <opencv2/opencv.hpp>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -69,6 +70,99 @@ Mat operator-(const Mat& a, const Mat& b)
         for (int x = 0; x < a.cols; ++x) pr[x] = pa[x] - pb[x];
     }
     return r;
+}
+
+Mat& Mat::operator=(const Scalar& sc)
+{
+    need(channels() == 1, "Mat = Scalar on a 1-channel Mat");
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            if (depth() == CV_8U) at<uchar>(y, x) = (uchar)sc.val[0];
+            else if (depth() == CV_32S) at<int>(y, x) = (int)sc.val[0];
+            else at<float>(y, x) = (float)sc.val[0];
+        }
+    return *this;
+}
+
+void Mat::convertTo(Mat& dst, int rtype, double alpha, double beta) const
+{
+    const int cn = channels(), sd = depth(), dd = CV_MAT_DEPTH(rtype);
+    Mat out(rows, cols, CV_MAKETYPE(dd, cn));
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols * cn; ++x) {
+            if (sd == CV_8U && dd == CV_32S) { need(alpha == 1.0 && beta == 0.0, "convertTo scale"); out.ptr<int>(y)[x] = ptr<uchar>(y)[x]; }
+            else if (sd == CV_32S && dd == CV_8U) { need(alpha == 1.0 && beta == 0.0, "convertTo scale"); int v = ptr<int>(y)[x]; out.ptr<uchar>(y)[x] = (uchar)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+            else if (sd == CV_32F && dd == CV_8U) {  // cv::saturate_cast<uchar>(cvRound(v*alpha+beta)), float arithmetic, round-half-even
+                const float v = ptr<float>(y)[x] * (float)alpha + (float)beta;
+                const long r = lrintf(v);
+                out.ptr<uchar>(y)[x] = (uchar)(r < 0 ? 0 : (r > 255 ? 255 : r));
+            } else need(false, "convertTo: unsupported depth pair");
+        }
+    dst = out;
+}
+
+void split(const Mat& src, std::vector<Mat>& mv)
+{
+    need(src.channels() == 1, "split(vector) of a 1-channel Mat");
+    mv.assign(1, src.clone());
+}
+
+void merge(const std::vector<Mat>& mv, Mat& dst)
+{
+    need(mv.size() == 1, "merge of one channel");
+    dst = mv[0].clone();
+}
+
+void minMaxLoc(const Mat& src, double* minVal, double* maxVal)
+{
+    need(src.type() == CV_32FC1, "minMaxLoc(CV_32FC1)");
+    double lo = DBL_MAX, hi = -DBL_MAX;
+    for (int y = 0; y < src.rows; ++y)
+        for (int x = 0; x < src.cols; ++x) { const double v = src.at<float>(y, x); lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
+    if (minVal) *minVal = lo;
+    if (maxVal) *maxVal = hi;
+}
+
+double kmeans(const Mat& samples, int K, Mat& labels, TermCriteria, int, int, Mat& centers)
+{
+    need(samples.type() == CV_32FC1 && samples.cols == 3 && K >= 1 && K <= samples.rows, "kmeans(N x 3 CV_32F)");
+    const int N = samples.rows;
+    labels.create(N, 1, CV_32SC1);
+    centers.create(K, 3, CV_32FC1);
+    if (K == N) {   // every sample is its own centre: exact, order-independent
+        for (int i = 0; i < N; ++i) { labels.at<int>(i, 0) = i; std::memcpy(centers.ptr<float>(i), samples.ptr<float>(i), 12); }
+        return 0.0;
+    }
+    // deterministic stand-in (NOT cv::kmeans): farthest-point seeding from sample 0, then two Lloyd iterations
+    std::vector<float> best(N, 3.4e38f);
+    int pick = 0;
+    for (int k = 0; k < K; ++k) {
+        std::memcpy(centers.ptr<float>(k), samples.ptr<float>(pick), 12);
+        float far = -1.f; int arg = 0;
+        for (int i = 0; i < N; ++i) {
+            const float* sp = samples.ptr<float>(i); const float* c = centers.ptr<float>(k);
+            const float d = (sp[0]-c[0])*(sp[0]-c[0]) + (sp[1]-c[1])*(sp[1]-c[1]) + (sp[2]-c[2])*(sp[2]-c[2]);
+            if (d < best[i]) best[i] = d;
+            if (best[i] > far) { far = best[i]; arg = i; }
+        }
+        pick = arg;
+    }
+    for (int it = 0; it < 2; ++it) {
+        std::vector<double> acc((size_t)K * 3, 0.0); std::vector<int> cnt(K, 0);
+        for (int i = 0; i < N; ++i) {
+            const float* sp = samples.ptr<float>(i); float bd = 3.4e38f; int bk = 0;
+            for (int k = 0; k < K; ++k) {
+                const float* c = centers.ptr<float>(k);
+                const float d = (sp[0]-c[0])*(sp[0]-c[0]) + (sp[1]-c[1])*(sp[1]-c[1]) + (sp[2]-c[2])*(sp[2]-c[2]);
+                if (d < bd) { bd = d; bk = k; }
+            }
+            labels.at<int>(i, 0) = bk; cnt[bk]++;
+            for (int c3 = 0; c3 < 3; ++c3) acc[(size_t)bk * 3 + c3] += sp[c3];
+        }
+        if (it == 0)
+            for (int k = 0; k < K; ++k) if (cnt[k]) for (int c3 = 0; c3 < 3; ++c3) centers.at<float>(k, c3) = (float)(acc[(size_t)k * 3 + c3] / cnt[k]);
+    }
+    return 0.0;
 }
 
 void split(const Mat& src, Mat* mv)

@@ -455,3 +455,73 @@ int orc_pipeline(const float* lImg, const float* rImg, int W, int H, int D, int 
     free(lGrd); free(rGrd);
     return rc;
 }
+
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Post-processing: the joint weighted-median filter of the disparity maps (PP::processDM, src/PP.cpp:402-425:
+ * img.convertTo(CV_8UC3, 255) then JointWMF::filter(disp, img8UC3, MED_SZ/2 = 9), include/JointWMF.h:81-155).
+ *
+ * PARITY UNPINNED for natural images: the reference clusters the feature colours with cv::kmeans (k-means++ on
+ * cv::theRNG(), JointWMF.h:586-591; un-vendored, RNG-seeded) down to nF = 256 indices and documents the result as an
+ * approximation (JointWMF.h:70-72).  This restatement is the filter WITHOUT that approximation -- the weight between
+ * two pixels is taken between their own 6-bit colours (what the reference computes when the image has <= 256 distinct
+ * 6-bit colours, where every colour is its own cluster) -- with the definition of the output the reference's cut-point
+ * search implements (JointWMF.h:257-316):  out = min { v : sum_{I_q <= v} w_q  >=  sum_{I_q > v} w_q }  over the
+ * (2r+1)^2 window clipped at the image border (JointWMF.h:207-211, 322-325).
+ * Weights: w = exp(-(d0^2+d1^2+d2^2) * divider), divider = 1/(2 s^2), s = 25.5/256*64 (JointWMF.h:620-641), evaluated
+ * in float exactly like the reference and then held as 2^-22 fixed point so that the sums are exact integers,
+ * independent of summation order (the reference's float sums depend on its necklace-table insertion history).
+ * -------------------------------------------------------------------------------------------------------------- */
+#define ORC_PP_MAXD2 (3 * 63 * 63)
+void orc_pp_weight_lut(uint32_t* lut /* ORC_PP_MAXD2 + 1 */)
+{
+    const float nSigmaI = 25.5f / 256.0f * 64;
+    const float divider = (1.0f / (2 * nSigmaI * nSigmaI));
+    for (int d2 = 0; d2 <= ORC_PP_MAXD2; ++d2) {
+        const float w = expf(-(float)d2 * divider);
+        lut[d2] = (uint32_t)lrintf(w * 4194304.0f);
+    }
+}
+
+/* img8: interleaved BGR u8 (the CV_8UC3 feature image), disp: u8 map, out: u8 map (may not alias disp) */
+void orc_wmf(const uint8_t* disp, const uint8_t* img8, int W, int H, int r, uint8_t* out)
+{
+    uint32_t* lut = (uint32_t*)malloc((ORC_PP_MAXD2 + 1) * sizeof(uint32_t));
+    orc_pp_weight_lut(lut);
+    for (int y = 0; y < H; ++y) {
+        for (int x = 0; x < W; ++x) {
+            uint64_t hist[256];
+            memset(hist, 0, sizeof(hist));
+            const uint8_t* cp = img8 + ((size_t)y * W + x) * 3;
+            const int b = cp[0] >> 2, g = cp[1] >> 2, rr = cp[2] >> 2;
+            uint64_t total = 0;
+            const int y0 = y - r < 0 ? 0 : y - r, y1 = y + r > H - 1 ? H - 1 : y + r;
+            const int x0 = x - r < 0 ? 0 : x - r, x1 = x + r > W - 1 ? W - 1 : x + r;
+            for (int yy = y0; yy <= y1; ++yy)
+                for (int xx = x0; xx <= x1; ++xx) {
+                    const uint8_t* cq = img8 + ((size_t)yy * W + xx) * 3;
+                    const int d0 = b - (cq[0] >> 2), d1 = g - (cq[1] >> 2), d2 = rr - (cq[2] >> 2);
+                    const uint32_t w = lut[d0 * d0 + d1 * d1 + d2 * d2];
+                    hist[disp[(size_t)yy * W + xx]] += w;
+                    total += w;
+                }
+            uint64_t cum = 0;
+            int v = 0;
+            for (; v < 255; ++v) {
+                cum += hist[v];
+                if (2 * cum >= total) break;
+            }
+            out[(size_t)y * W + x] = (uint8_t)v;
+        }
+    }
+    free(lut);
+}
+
+/* lImg.convertTo(lImg_8UC3, CV_8UC3, 255) (src/PP.cpp:416-417): saturate_cast<uchar>(cvRound(v * 255)) */
+void orc_f32_to_u8x255(const float* src, uint8_t* dst, size_t n)
+{
+    for (size_t i = 0; i < n; ++i) {
+        const long q = lrintf(src[i] * 255.0f);
+        dst[i] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+    }
+}

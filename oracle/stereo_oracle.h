@@ -91,6 +91,12 @@ int orc_pipeline(const float* lImg, const float* rImg, int W, int H, int D, int 
                  int gray_mode, float* lVol, float* rVol, uint8_t* lDis, uint8_t* rDis,
                  double* times_ms);
 
+/* Post-processing (PP::processDM live code, src/PP.cpp:414-422 -> JointWMF::filter): see stereo_oracle.c.
+ * PARITY UNPINNED for natural images (cv::kmeans feature clustering is RNG-seeded); this is the un-clustered filter. */
+void orc_pp_weight_lut(uint32_t* lut /* 3*63*63 + 1 entries, 2^-22 fixed point */);
+void orc_wmf(const uint8_t* disp, const uint8_t* img8_bgr, int W, int H, int r, uint8_t* out);
+void orc_f32_to_u8x255(const float* src, uint8_t* dst, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

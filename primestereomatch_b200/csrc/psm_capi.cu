@@ -8,7 +8,10 @@
 #include <cstring>
 #include <new>
 
+#include <cmath>
+
 #include "psm_cvf_stream.cuh"
+#include "psm_pp.cuh"
 
 #ifndef PSM_BUILD_FLAGS
 #define PSM_BUILD_FLAGS "unknown"
@@ -18,7 +21,7 @@ using namespace psm;
 
 namespace {
 
-constexpr int kNumStages = 5;  // ingest, cvc, cvf, wta, cvf-filter-kernel
+constexpr int kNumStages = 6;  // ingest, cvc, cvf, wta, cvf-filter-kernel, post-process
 
 thread_local char g_create_error[512] = "";  // per host thread: psm_last_error(NULL) reports the calling thread's last failed creation
 
@@ -41,6 +44,10 @@ struct psm_ctx {
     int stage_cur = 0;                      // staging set holding the current frame: 0 = stage_in, 1 = stage_alt
     int up_pending = 0;                     // 0 none, 1 f32 upload pending, 2 u8 upload pending
     uint8_t* dis[2] = {nullptr, nullptr};
+    uint8_t* dis_pp[2] = {nullptr, nullptr}; // post-processed maps
+    uint32_t* pp_packed = nullptr;          // packed (disparity, 6-bit colour) image of one view, lazy
+    uint32_t* pp_lut = nullptr;             // weight table indexed by squared colour distance, lazy
+    bool have_maps = false;                 // disparity maps valid (a select / reduce stage ran)
     int* guide_flags = nullptr;             // [2] device flags: guide outside the integer-widening domain (see psm_cvf_stream.cuh)
     unsigned char* p2p_own = nullptr;       // own exchange block: keys [2 views][nranks][chunk] u64, maps [2 views][H*W] u8, flag words
     unsigned char* p2p_peer[kMaxRanks] = {};// every rank's exchange block as mapped here
@@ -245,7 +252,7 @@ int launch_cvf_stream(psm_ctx* c)
     //   variants 5-8: experiments recorded in DESIGN.md section 9 (prefetch on/off, stage-2 F2F, 144/152-register builds)
     using kern_t = void (*)(CvfParams);
     kern_t kern = nullptr;
-    bool tm = true;
+    bool tm = true, staged = false;
     if (c->cvf_mode == PSM_CVF_MIXED) {
         switch (c->cvf_variant) {
         case 2: kern = cvf_stream_kernel<3, 1, kS2Mixed, 0>; tm = false; break;
@@ -254,6 +261,7 @@ int launch_cvf_stream(psm_ctx* c)
         case 6: kern = cvf_stream_kernel<4, 1, kS2Mixed, 1, 1>; break;
         case 7: kern = cvf_stream_kernel<5, 1, kS2Mixed, 1, 0>; break;   // 144 registers
         case 8: kern = cvf_stream_kernel<6, 1, kS2Mixed, 1, 0>; break;   // 152 registers
+        case 9: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1, 2>; staged = true; break;   // TMA-staged guide rows
         default: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1>; break;
         }
     } else {
@@ -265,12 +273,13 @@ int launch_cvf_stream(psm_ctx* c)
         case 6: kern = cvf_stream_kernel<3, 2, kS2Exact, 1, 0>; break;
         case 7: kern = cvf_stream_kernel<3, 2, kS2Exact, 1, 1>; break;
         case 8: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 0>; break;
+        case 9: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 2>; staged = true; break;   // TMA-staged guide rows
         default: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 1>; break;
         }
     }
-    const size_t smem = (tm ? 0 : (size_t)8 * 4 * nthreads * sizeof(float4)) + (size_t)c->cvf_extra_smem;
+    const size_t smem = (tm ? (staged ? (size_t)kStSmemBytes : 0) : (size_t)8 * 4 * nthreads * sizeof(float4)) + (size_t)c->cvf_extra_smem;
     PSM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (tm && !c->cvf_extra_smem)  // nothing lives in shared memory: give the whole array to L1 (the guide rows are re-read by every slice)
+    if (tm && !staged && !c->cvf_extra_smem)  // nothing lives in shared memory: give the whole array to L1 (the guide rows are re-read by every slice)
         PSM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
     P.guide_flags = c->guide_flags;
     const unsigned grid = 2u * P.nseg * P.nstrips * P.ndgroups;
@@ -395,6 +404,8 @@ int psm_destroy(psm_ctx* c)
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->ab);
     cudaFree(c->guide_flags);
+    cudaFree(c->pp_packed); cudaFree(c->pp_lut);
+    for (int v = 0; v < 2; ++v) cudaFree(c->dis_pp[v]);
     for (int s = 0; s < kNumStages; ++s) {
         if (c->ev0[s]) cudaEventDestroy(c->ev0[s]);
         if (c->ev1[s]) cudaEventDestroy(c->ev1[s]);
@@ -515,8 +526,9 @@ int psm_cost_const(psm_ctx* c)
     if (int rc = bind(c)) return rc;
     if (!c->have_images) return fail(c, PSM_ESTATE, "psm_cost_const before psm_set_images");
     if (int rc = stage_begin(c, 1)) return rc;
+    CvcParams2 P2;
     for (int v = 0; v < 2; ++v) {
-        CvcParams P;
+        CvcParams& P = P2.v[v];
         const float* gs = c->guide[v];
         const float* go = c->guide[1 - v];
         for (int k = 0; k < 3; ++k) { P.self[k] = gs + k * c->plane; P.other[k] = go + k * c->plane; }
@@ -525,12 +537,14 @@ int psm_cost_const(psm_ctx* c)
         P.vol = c->vol[v];
         P.W = c->W; P.H = c->H; P.Wp = c->Wp; P.d_begin = c->d_begin; P.d_count = c->d_count;
         P.fold_halo = c->W >= 32 ? 1 : 0;
-        dim3 blk(128), grd((((c->W + 3) / 4) + 127) / 128, c->H);
-        if (v == PSM_LEFT) cvc_kernel<-1><<<grd, blk, 0, c->stream>>>(P);
-        else cvc_kernel<+1><<<grd, blk, 0, c->stream>>>(P);
+    }
+    {
+        dim3 blk(128), grd((((c->W + 3) / 4) + 127) / 128, c->H, 2);
+        cvc_both_kernel<<<grd, blk, 0, c->stream>>>(P2);
         PSM_LAUNCH_CHECK(c);
-        if (!P.fold_halo)  // narrow images: separate halo pass (general reflection)
-            if (int rc = pad_rows(c, c->vol[v], (size_t)c->d_count * c->H)) return rc;
+        if (!P2.v[0].fold_halo)  // narrow images: separate halo pass (general reflection)
+            for (int v = 0; v < 2; ++v)
+                if (int rc = pad_rows(c, c->vol[v], (size_t)c->d_count * c->H)) return rc;
     }
     c->have_cvc = true;
     c->filtered = false;
@@ -581,6 +595,7 @@ int psm_disp_select_device(psm_ctx* c)
         wta_kernel<<<grd, blk, 0, c->stream>>>(c->vol[v], c->W, c->H, c->Wp, c->d_begin, c->d_count, c->dis[v], nullptr);
         PSM_LAUNCH_CHECK(c);
     }
+    c->have_maps = true;
     return stage_end(c, 3);
 }
 
@@ -628,6 +643,7 @@ int psm_disp_reduce_keys(psm_ctx* c, const uint64_t* d_gathered_left, const uint
             reinterpret_cast<const unsigned long long*>(g[v]), nranks, npix, c->dis[v]);
         PSM_LAUNCH_CHECK(c);
     }
+    c->have_maps = true;
     if (left && right) {
         if (int rc = copy_map_out(c, c->dis[0], left, left_step)) return rc;
         if (int rc = copy_map_out(c, c->dis[1], right, right_step)) return rc;
@@ -760,6 +776,57 @@ int psm_disp_fetch_p2p(psm_ctx* c, uint8_t* left, size_t left_step, uint8_t* rig
     return PSM_OK;
 }
 
+// ---- post-processing (PP::processDM) ----------------------------------------------------------------
+static const uint8_t* current_map(const psm_ctx* c, int v)
+{
+    if (c->p2p_own && c->p2p_seq > 0)   // sharded: the complete maps live in the exchange block
+        return c->p2p_own + p2p_keys_bytes(c, c->p2p_nranks) + (size_t)v * c->W * c->H;
+    return c->dis[v];
+}
+
+int psm_post_process_device(psm_ctx* c)
+{
+    if (int rc = bind(c)) return rc;
+    if (!c->have_images) return fail(c, PSM_ESTATE, "psm_post_process before psm_set_images");
+    if (!c->have_maps && !(c->p2p_own && c->p2p_seq > 0)) return fail(c, PSM_ESTATE, "psm_post_process before a disparity-selection stage");
+    const size_t npix = (size_t)c->W * c->H;
+    if (!c->pp_lut) {
+        // weight table: the reference's float expression (JointWMF.h:620-641, "exp" weights, sigma 25.5, 64 levels)
+        uint32_t* host = new (std::nothrow) uint32_t[kPpMaxD2 + 1];
+        if (!host) return fail(c, PSM_ENOMEM, "out of host memory");
+        const float nSigmaI = 25.5f / 256.0f * 64;
+        const float divider = (1.0f / (2 * nSigmaI * nSigmaI));
+        for (int d2 = 0; d2 <= kPpMaxD2; ++d2) host[d2] = (uint32_t)lrintf(expf(-(float)d2 * divider) * 4194304.0f);
+        cudaError_t e = cudaMalloc(&c->pp_lut, (kPpMaxD2 + 1) * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemcpy(c->pp_lut, host, (kPpMaxD2 + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice);
+        delete[] host;
+        PSM_CUDA(c, e);
+        PSM_CUDA(c, cudaMalloc(&c->pp_packed, npix * sizeof(uint32_t)));
+        for (int v = 0; v < 2; ++v) PSM_CUDA(c, cudaMalloc(&c->dis_pp[v], npix));
+    }
+    if (int rc = stage_begin(c, 5)) return rc;
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+    for (int v = 0; v < 2; ++v) {
+        const float* g = c->guide[v];
+        dim3 blk(256), grd((c->W + 255) / 256, c->H);
+        pp_pack_kernel<<<grd, blk, 0, c->stream>>>(g, g + c->plane, g + 2 * c->plane, c->Wp, current_map(c, v), c->W, c->H, c->pp_packed);
+        PSM_LAUNCH_CHECK(c);
+        pp_wmf_kernel<<<nsm * 8, kPpWarps * 32, 0, c->stream>>>(c->pp_packed, c->pp_lut, c->W, c->H, c->dis_pp[v]);
+        PSM_LAUNCH_CHECK(c);
+    }
+    return stage_end(c, 5);
+}
+
+int psm_post_process(psm_ctx* c, uint8_t* left, size_t left_step, uint8_t* right, size_t right_step)
+{
+    if (int rc = psm_post_process_device(c)) return rc;
+    if (int rc = copy_map_out(c, c->dis_pp[0], left, left_step)) return rc;
+    if (int rc = copy_map_out(c, c->dis_pp[1], right, right_step)) return rc;
+    PSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PSM_OK;
+}
+
 static int check_slice(psm_ctx* c, int view, int d)
 {
     if (view != PSM_LEFT && view != PSM_RIGHT) return fail(c, PSM_EINVAL, "bad view %d", view);
@@ -841,6 +908,7 @@ int psm_device_ptr(psm_ctx* c, int what, void** ptr, size_t* pitch_elems)
     switch (what) {
     case 0: case 1: *ptr = c->vol[what]; if (pitch_elems) *pitch_elems = c->Wp; return PSM_OK;
     case 2: case 3: *ptr = c->dis[what - 2]; if (pitch_elems) *pitch_elems = c->W; return PSM_OK;
+    case 4: case 5: *ptr = c->dis_pp[what - 4]; if (pitch_elems) *pitch_elems = c->W; return PSM_OK;
     default: return fail(c, PSM_EINVAL, "bad selector %d", what);
     }
 }

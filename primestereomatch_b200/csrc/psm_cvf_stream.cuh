@@ -194,12 +194,52 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 constexpr unsigned kTmemCols = 128;   // one ring = 128 columns of one lane quarter; a CTA allocates one block per 4 warps
 
+
+// ---- TMA (bulk async copy) staging of the guide rows --------------------------------------------
+// The 13 guide rows a step needs (10 coefficient planes at the a,b columns, 3 image planes at the
+// input columns) are identical for every slice-warp of a CTA.  One elected lane of warp 0 copies them
+// global -> shared with cp.async.bulk (the TMA engine; one 512/544-byte row per instruction) two steps
+// ahead; completion is signalled on an mbarrier (complete_tx), consumption on a second mbarrier with
+// one arrival per warp.  Consumers read with LDS at immediate offsets: no per-load address arithmetic,
+// no L2 latency on the critical path, and the image rows (needed as newest, output and oldest row of
+// the stage-1 window) stay in a 16-row ring, so they are fetched from L2 once per CTA instead of
+// three times per warp.
+constexpr int kStCoefStages = 4;       // coefficient stages in flight (power of two)
+constexpr int kStIRows = 16;           // image-row ring (power of two >= 8 + stages)
+constexpr int kStLook = 2;             // the producer runs this many steps ahead
+constexpr int kStIRowFloats = 136;     // 128 input columns + 8 so that the output columns (+8) stay inside the row
+constexpr int kStBarBytes = 128;
+constexpr int kStCoefBytes = kStCoefStages * 10 * 128 * 4;
+constexpr int kStIBytes = kStIRows * 3 * kStIRowFloats * 4;
+constexpr int kStSmemBytes = kStBarBytes + kStCoefBytes + kStIBytes;
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}"
+                 :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 lds4(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 // MINB: resident CTAs per SM the register allocation is sized for (3 -> <=168 regs, 4 -> <=128);
 // IW  : 0 = F2F everywhere; 1 = integer widening into the scaled domain in both stages; 2 = integer widening in
 //       stage 1 (non-negative values: one instruction each), F2F in the exact stage 2 (signed values would cost three)
 // S2M : kS2Exact / kS2Mixed
 // TM  : 1 = history ring in tensor memory (tcgen05.ld/st), 0 = in shared memory
-// PF  : 1 = prefetch the next step's guide rows into L1
+// PF  : 1 = prefetch the next step's guide rows into L1;  2 = stage the guide rows in shared memory with bulk async
+//       copies (TMA) issued two steps ahead by one lane per CTA (needs TM = 1: the ring is not in shared memory)
 // register budgets by MINB: 3 -> 168 regs (3 CTAs x 128 thr or 4 x 96: 12 warps/SM); 4 -> 128 regs (16 warps);
 // 5 -> 144 regs (2 CTAs x 224 thr = 14 warps, two TMEM column blocks per lane quarter); 6 -> 152 regs (13 warps)
 constexpr int cvf_max_regs(int minb) { return minb == 3 ? 168 : (minb == 4 ? 128 : (minb == 5 ? 144 : 152)); }
@@ -234,6 +274,14 @@ cvf_stream_kernel(const CvfParams P)
     const int dlc_raw = dgroup * wpc + warp;
     const bool active = dlc_raw < P.Dloc;
     const int dlc = active ? dlc_raw : P.Dloc - 1;
+    constexpr bool ST = (PF == 2);
+    const unsigned st_base = (unsigned)__cvta_generic_to_shared(ring);   // staging area (ST): barriers, coefficient stages, image-row ring
+    if (ST && tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kStCoefStages; ++i) { mbar_init(st_base + 8 * i, 1); mbar_init(st_base + 8 * (kStCoefStages + i), wpc); }
+        mbar_init(st_base + 8 * 2 * kStCoefStages, 1);   // prologue barrier
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     unsigned tring = 0;   // TMEM address of this warp's ring (lane quarter = warp % 4, column block = warp / 4)
     // columns this CTA allocates: one 128-column block per group of 4 warps, rounded up to a power of two
     const unsigned tmem_cols = wpc <= 4 ? kTmemCols : (wpc <= 8 ? 2 * kTmemCols : 4 * kTmemCols);
@@ -629,13 +677,120 @@ cvf_stream_kernel(const CvfParams P)
             }
             ro_y += rowB;
         };
-        if (IW) {
-            for (; t <= Ts1 && !slow; ++t) {
-                if (needs_slow(xn.p, xo.p)) { slow = true; break; }
-                steady(std::false_type{});
+        if (!ST) {
+            if (IW) {
+                for (; t <= Ts1 && !slow; ++t) {
+                    if (needs_slow(xn.p, xo.p)) { slow = true; break; }
+                    steady(std::false_type{});
+                }
             }
+            for (; t <= Ts1; ++t) steady(std::true_type{});
+        } else {
+            // ---- steady loop with TMA-staged guide rows -------------------------------------------------
+            const int t_s = t, klast = Ts1 - t_s;
+            const unsigned bar_full = st_base, bar_empty = st_base + 8 * kStCoefStages, bar_pro = st_base + 8 * 2 * kStCoefStages;
+            const unsigned coef_s = st_base + kStBarBytes, iring_s = coef_s + kStCoefBytes;
+            const float* gbase = P.guide[view];
+            const unsigned lane16 = (unsigned)lane * 16u;
+            auto issue = [&](int k) {   // one lane: the 13 rows of step k -> stage k & 3 / image-row slot (t_s+k+3) & 15
+                const int sidx = k & (kStCoefStages - 1);
+                const unsigned bar = bar_full + 8 * sidx;
+                const int tt = t_s + k;
+                mbar_expect_tx(bar, 10 * 512 + 3 * kStIRowFloats * 4);
+#pragma unroll
+                for (int q = 0; q < 10; ++q)
+                    bulk_g2s(coef_s + (unsigned)((sidx * 10 + q) * 512), gbase + (size_t)(kGuideMean + q) * plane + (size_t)tt * Wp + (X0 - 4), 512, bar);
+                const int ri = tt + 3;
+#pragma unroll
+                for (int c3 = 0; c3 < 3; ++c3)
+                    bulk_g2s(iring_s + (unsigned)((((ri & (kStIRows - 1)) * 3 + c3) * kStIRowFloats) * 4),
+                             gbase + (size_t)c3 * plane + (size_t)ri * Wp + (X0 - 8), kStIRowFloats * 4, bar);
+            };
+            if (warp == 0 && lane == 0) {   // prologue: image rows t_s-4 .. t_s+2 and the first kStLook stages
+                mbar_expect_tx(bar_pro, 7 * 3 * kStIRowFloats * 4);
+                for (int ri = t_s - 4; ri <= t_s + 2; ++ri)
+#pragma unroll
+                    for (int c3 = 0; c3 < 3; ++c3)
+                        bulk_g2s(iring_s + (unsigned)((((ri & (kStIRows - 1)) * 3 + c3) * kStIRowFloats) * 4),
+                                 gbase + (size_t)c3 * plane + (size_t)ri * Wp + (X0 - 8), kStIRowFloats * 4, bar_pro);
+                for (int k = 0; k < kStLook && k <= klast; ++k) issue(k);
+            }
+            mbar_wait(bar_pro, 0);
+            auto irow = [&](int r) { return iring_s + (unsigned)(((r & (kStIRows - 1)) * 3 * kStIRowFloats) * 4) + lane16; };
+            auto steady_st = [&](auto slow_tag) {
+                constexpr bool SLOW = decltype(slow_tag)::value;
+                const int k = t - t_s;
+                if (warp == 0 && k + kStLook <= klast) {   // producer: refill the stage that every warp released four steps ago
+                    const int kk = k + kStLook;
+                    if (kk >= kStCoefStages) mbar_wait(bar_empty + 8 * (kk & (kStCoefStages - 1)), ((kk >> 2) + 1) & 1);
+                    if (lane == 0) issue(kk);
+                    __syncwarp();
+                }
+                mbar_wait(bar_full + 8 * (k & (kStCoefStages - 1)), (k >> 2) & 1);
+                f2x2 av[4];
+                {
+                    const unsigned cs = coef_s + (unsigned)((k & (kStCoefStages - 1)) * 10 * 512) + lane16;
+                    const unsigned inew = irow(t + 3), iold = irow(t - 4);
+                    RowIn x;
+                    x.p = xn.p; x.i0 = lds4(inew); x.i1 = lds4(inew + kStIRowFloats * 4); x.i2 = lds4(inew + 2 * kStIRowFloats * 4);
+                    add_row(x, SLOW);
+                    ro_n += rowB;
+                    xn.p = ldg4(vin + ro_n);
+                    float4 g4[10];
+#pragma unroll
+                    for (int q = 0; q < 10; ++q) g4[q] = lds4(cs + q * 512);
+                    coeffs(g4, av);
+                    x.p = xo.p; x.i0 = lds4(iold); x.i1 = lds4(iold + kStIRowFloats * 4); x.i2 = lds4(iold + 2 * kStIRowFloats * 4);
+                    sub_row(x, SLOW);
+                    ro_o += rowB;
+                    xo.p = ldg4(vin + ro_o);
+                }
+                const unsigned iout = irow(t - 3) + 32u;   // output columns = input columns + 8
+                const float4 o0 = lds4(iout), o1 = lds4(iout + kStIRowFloats * 4), o2 = lds4(iout + 2 * kStIRowFloats * 4);
+                if (!MIXED) {
+                    f2x2 old[4];
+                    ring_wait_st();
+                    ring_ld(t & 7, old);
+                    ring_wait_ld();
+                    ring_st(t & 7, av);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            S2[MIXED ? 0 : q][j] = __dsub_rn(__dadd_rn(S2[MIXED ? 0 : q][j], w2(get(av[q], j), SLOW)), w2(get(old[q], j), SLOW));
+                    }
+                    emit(ro_y, o0, o1, o2);
+                } else {
+                    f2x2 pa[4], pb[4], pc[4], pd[4];
+                    ring_wait_st();
+                    ring_ld((t - 6) & 7, pa);
+                    ring_ld((t - 4) & 7, pb);
+                    ring_wait_ld();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pa[q] = addp(pa[q], pb[q]);
+                    ring_ld((t - 2) & 7, pc);
+                    ring_ld(t & 7, pd);
+                    ring_wait_ld();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pd[q] = add2(av[q], pd[q]);
+                    ring_st(t & 7, pd);
+                    ring_st((t + 1) & 7, av);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pc[q] = addp(pc[q], pd[q]);
+                    emit_pairs(ro_y, pa, pc, o0, o1, o2);
+                }
+                ro_y += rowB;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * (k & (kStCoefStages - 1)));   // this warp is done with stage k
+            };
+            if (IW) {
+                for (; t <= Ts1 && !slow; ++t) {
+                    if (needs_slow(xn.p, xo.p)) { slow = true; break; }
+                    steady_st(std::false_type{});
+                }
+            }
+            for (; t <= Ts1; ++t) steady_st(std::true_type{});
         }
-        for (; t <= Ts1; ++t) steady(std::true_type{});
     }
     for (; t <= Tend; ++t) generic_step(t);
     if (TM) {

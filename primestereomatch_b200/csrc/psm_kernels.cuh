@@ -114,7 +114,21 @@ __device__ __forceinline__ float cost_border(float l0, float l1, float l2, float
 }
 
 template <int SIGN>
-__global__ void __launch_bounds__(128) cvc_kernel(CvcParams P)
+__device__ __forceinline__ void cvc_body(const CvcParams& P);
+
+// both volumes in ONE launch (blockIdx.z = view): twice the CTAs in flight and no tail between the two views
+struct CvcParams2 { CvcParams v[2]; };
+__global__ void __launch_bounds__(128) cvc_both_kernel(const CvcParams2 P2)
+{
+    if (blockIdx.z == 0) cvc_body<-1>(P2.v[0]);
+    else cvc_body<+1>(P2.v[1]);
+}
+
+template <int SIGN>
+__global__ void __launch_bounds__(128) cvc_kernel(CvcParams P) { cvc_body<SIGN>(P); }
+
+template <int SIGN>
+__device__ __forceinline__ void cvc_body(const CvcParams& P)
 {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
@@ -174,7 +188,7 @@ __global__ void __launch_bounds__(128) cvc_kernel(CvcParams P)
             rp[j] = (x < W) ? (interior ? c : bord[j]) : 0.f;
         }
         float* o = out + (size_t)dl * slice;
-        if (full_group) *reinterpret_cast<float4*>(o) = r;
+        if (full_group) __stcs(reinterpret_cast<float4*>(o), r);   // streaming store: 2 GB per frame, next touched by the CVF kernel from HBM
         else {  // last, partial group of a row: columns >= W belong to the mirrored halo
 #pragma unroll
             for (int j = 0; j < 4; ++j) if (x4 + j < W) o[j] = rp[j];

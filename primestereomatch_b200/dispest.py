@@ -131,8 +131,12 @@ class DispEst:
         return 0
 
     def PostProcess_GPU(self):
-        """DispEst.cpp:338-344 runs the CPU JointWMF even in GPU mode; out of scope here."""
-        raise NotImplementedError("post-processing (PP.cpp / JointWMF) is outside the accelerated path")
+        """DispEst.cpp:338-344 -> PP::processDM (PP.cpp:402-425): joint weighted-median filter of both maps; the
+        reference runs it on the CPU even in GPU mode, here it is a device stage.  Results replace lDisMap / rDisMap."""
+        self._need_gpu()
+        capi.check(self._lib.psm_post_process(self._ctx, _ptr(self.lDisMap), self.lDisMap.strides[0],
+                                              _ptr(self.rDisMap), self.rDisMap.strides[0]), self._ctx)
+        return 0
 
     def CostConst(self):
         raise NotImplementedError("CPU stage (reference src/CVC.cpp) is not part of this package")

@@ -69,6 +69,13 @@ int DispEst::printCV(void)
 int DispEst::CostConst_GPU()
 {
     if (!ctx) return -1;
+    // the context was sized at construction: a differently shaped or typed Mat from setInputImages must not reach
+    // the 2-D copy (the reference re-creates DispEst on every dataset change, StereoMatch.cpp:601-602)
+    if (lImg.rows != hei || lImg.cols != wid || rImg.rows != hei || rImg.cols != wid || lImg.type() != rImg.type() ||
+        lImg.channels() != 3) {
+        std::fprintf(stderr, "DispEst::CostConst_GPU: input images must be %dx%d, 3 channels, equal types\n", wid, hei);
+        return -1;
+    }
     int rc;
     if ((lImg.type() & CV_MAT_DEPTH_MASK) == CV_32F)
         rc = psm_set_images(ctx, lImg.ptr<float>(), lImg.step, rImg.ptr<float>(), rImg.step);
@@ -92,9 +99,10 @@ int DispEst::DispSelect_GPU()
     return psm_disp_select(ctx, lDisMap.ptr<uint8_t>(), lDisMap.step, rDisMap.ptr<uint8_t>(), rDisMap.step);
 }
 
-// reference src/DispEst.cpp:338-344 calls the CPU JointWMF even in GPU mode; that post-filter is
-// outside the accelerated path and stays with the reference.
+// reference src/DispEst.cpp:338-344 -> PP::processDM (src/PP.cpp:402-425): the joint weighted-median filter of
+// both maps.  The reference runs it on the CPU even in GPU mode; here it is a device stage (psm_pp.cuh).
 int DispEst::PostProcess_GPU()
 {
-    return 0;
+    if (!ctx) return -1;
+    return psm_post_process(ctx, lDisMap.ptr<uint8_t>(), lDisMap.step, rDisMap.ptr<uint8_t>(), rDisMap.step);
 }

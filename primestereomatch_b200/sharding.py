@@ -120,29 +120,60 @@ class P2PExchange:
 class BandedUpload:
     """N > 1, frames in HOST memory: every rank uploads only its row band of both images over PCIe (H/N rows) and
     the bands are all-gathered over NVLink, so the host->device bytes per rank shrink with N instead of every
-    rank uploading both full images.  The gathered interleaved images feed psm_set_images_device."""
+    rank uploading both full images.  The gathered interleaved images feed psm_set_images_device.
+    upload_async() runs the band copies and the all-gathers on a side stream into the buffer set that is not in
+    use; commit() makes the context's stream wait for them and ingests -- frame k+1 uploads while frame k computes."""
 
     def __init__(self, de, world, rank, dtype="float32", group=None):
         import torch
+        if dtype != "float32":
+            raise ValueError("BandedUpload gathers float32 frames (psm_set_images_device takes float images)")
         self.de, self.world, self.rank, self.group = de, world, rank, group
         self.r0, self.r1, self.rows = band_rows(de.hei, world, rank)
-        tdt = torch.float32 if dtype == "float32" else torch.uint8
-        if tdt is not torch.float32:
-            raise ValueError("BandedUpload gathers float32 frames (psm_set_images_device takes float images)")
         W = de.wid
-        self.band = [torch.zeros((self.rows, W, 3), dtype=tdt, device="cuda") for _ in range(2)]
-        self.full = [torch.empty((world * self.rows, W, 3), dtype=tdt, device="cuda") for _ in range(2)]
+        self.band = [torch.zeros((self.rows, W, 3), dtype=torch.float32, device="cuda") for _ in range(2)]
+        self.full = [[torch.empty((world * self.rows, W, 3), dtype=torch.float32, device="cuda") for _ in range(2)]
+                     for _ in range(2)]
         self.step_bytes = W * 3 * 4
-        bind_to_current_stream(de)   # the all-gathers and the ingest kernels share one stream
+        self.side = torch.cuda.Stream()
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [None, None]
+        self.cur, self.pending = 0, None
+        bind_to_current_stream(de)   # the ingest kernels run on torch's current stream, which waits for the side stream
 
     def h2d_bytes(self):
         return 2 * (self.r1 - self.r0) * self.de.wid * 3 * 4
 
-    def upload(self, left_pinned, right_pinned):
+    def upload_async(self, left_pinned, right_pinned):
         """left_pinned / right_pinned: pinned host tensors [H, W, 3] float32 of the FULL frame (each rank reads its band)."""
+        import torch
         import torch.distributed as dist
-        for k, src in enumerate((left_pinned, right_pinned)):
-            self.band[k][: self.r1 - self.r0].copy_(src[self.r0:self.r1], non_blocking=True)
-            dist.all_gather_into_tensor(self.full[k].view(-1), self.band[k].view(-1), group=self.group)
-        capi.check(capi.lib().psm_set_images_device(self.de.handle, self.full[0].data_ptr(), self.step_bytes,
-                                                    self.full[1].data_ptr(), self.step_bytes), self.de.handle)
+        if self.pending is not None:
+            raise RuntimeError("an upload is already pending: call commit() first")
+        s = self.cur ^ 1
+        with torch.cuda.stream(self.side):
+            if self.consumed[s] is not None:
+                self.side.wait_event(self.consumed[s])   # the ingest of the frame that last used this set is done
+            for k, src in enumerate((left_pinned, right_pinned)):
+                self.band[k][: self.r1 - self.r0].copy_(src[self.r0:self.r1], non_blocking=True)
+                dist.all_gather_into_tensor(self.full[s][k].view(-1), self.band[k].view(-1), group=self.group)
+            self.ready[s].record(self.side)
+        self.pending = s
+
+    def commit(self):
+        import torch
+        if self.pending is None:
+            raise RuntimeError("commit() without a pending upload_async()")
+        s, self.pending = self.pending, None
+        main = torch.cuda.current_stream()
+        main.wait_event(self.ready[s])
+        capi.check(capi.lib().psm_set_images_device(self.de.handle, self.full[s][0].data_ptr(), self.step_bytes,
+                                                    self.full[s][1].data_ptr(), self.step_bytes), self.de.handle)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.consumed[s] = ev
+        self.cur = s
+
+    def upload(self, left_pinned, right_pinned):
+        self.upload_async(left_pinned, right_pinned)
+        self.commit()

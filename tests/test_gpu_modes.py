@@ -15,7 +15,7 @@ from test_gpu_parity import assert_same, run_gpu
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 6])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 6, 9])
 def test_exact_variants_bit_exact(variant, scenes, oracle_scene_results):
     _, _, l, r = scenes["Teddy"]
     ref = oracle_scene_results["Teddy"]
@@ -26,7 +26,8 @@ def test_exact_variants_bit_exact(variant, scenes, oracle_scene_results):
     assert_same(g["rd"], ref["rd"], "rDisMap")
 
 
-def test_costs_outside_the_integer_domain(oracle):
+@pytest.mark.parametrize("variant", [0, 9])
+def test_costs_outside_the_integer_domain(variant, oracle):
     """Negative and -0 costs in a few rows (the rest of the volume is ordinary): the affected warps leave
     the integer-widening loop for the F2F loop mid-segment; everything stays bit-exact."""
     rng = np.random.default_rng(17)
@@ -40,6 +41,7 @@ def test_costs_outside_the_integer_domain(oracle):
     rgb, mean, var = oracle.cvf_preprocess(l)
     want = np.stack([oracle.guided_filter(rgb, mean, var, vol[d]) for d in range(D)])
     with DispEst(l, l, D) as de:
+        de.set_option(capi.PSM_OPT_VARIANT, variant)
         de.CostConst_GPU()
         for d in range(D):
             de.write_cost_slice(0, d, vol[d]); de.write_cost_slice(1, d, vol[d])
@@ -79,14 +81,16 @@ def test_mixed_mode_matches_its_model_and_tolerance(scene, scenes, oracle, oracl
         assert int((diff > 0).sum()) == 0          # in fact identical maps on both scenes
 
 
+@pytest.mark.parametrize("variant", [0, 9])
 @pytest.mark.parametrize("W,H,D", [(16, 16, 4), (17, 23, 5), (113, 40, 8), (130, 50, 9), (225, 33, 16),
                                    (451, 64, 12), (64, 300, 6), (340, 17, 3)])
-def test_mixed_mode_ragged_sizes(W, H, D, oracle):
+def test_mixed_mode_ragged_sizes(W, H, D, variant, oracle):
+    """variant 9 = guide rows staged in shared memory by bulk async copies (TMA); same results."""
     rng = np.random.default_rng(W * 1000 + H)
     l = rng.random((H, W, 3), dtype=np.float32)
     r = np.clip(np.roll(l, -3, axis=1) + rng.normal(0, 0.02, (H, W, 3)), 0, 1).astype(np.float32)
     _, _, lraw, rraw = oracle.cost_const(l, r, D)
-    g = run_gpu(l, r, D, mode=capi.PSM_CVF_MIXED)
+    g = run_gpu(l, r, D, mode=capi.PSM_CVF_MIXED, variant=variant)
     assert_same(g["lf"], MM.cost_filter_mixed(oracle, l, lraw), f"MIXED left {W}x{H}x{D}")
     assert_same(g["rf"], MM.cost_filter_mixed(oracle, r, rraw), f"MIXED right {W}x{H}x{D}")
 
