@@ -16,6 +16,7 @@
  *                                                                 src/DispEst.cpp:164-170, src/CVC_cl.cpp:93-160
  *   psm_cost_const        <-> DispEst::CostConst_GPU             src/DispEst.cpp:272-276
  *   psm_cost_filter       <-> DispEst::CostFilter_GPU            src/DispEst.cpp:299-308
+ *   psm_cost_filter_fgf   <-> DispEst::CostFilter_FGF -> FastGuidedFilter   src/DispEst.cpp:281-296, src/fastguidedfilter.cpp
  *   psm_disp_select       <-> DispEst::DispSelect_GPU + D2H in DispSel_cl::CVSelect
  *                                                                 src/DispEst.cpp:323-328, src/DispSel_cl.cpp:123-134
  *   psm_post_process      <-> DispEst::PostProcess_GPU -> PP::processDM -> JointWMF::filter
@@ -126,6 +127,13 @@ int psm_cost_const(psm_ctx* ctx);
 /* Stage 2: guide precompute + guided filter of every slice of both volumes, in place
  * (CostFilter_GPU). Asynchronous on the context stream. */
 int psm_cost_filter(psm_ctx* ctx);
+
+/* Stage 2, Fast-Guided-Filter variant (DispEst::CostFilter_FGF, what the reference's CPU branch runs today): every
+ * slice is sub-sampled by `sub_sample_rate` (1, 2, 4 or 8; the reference's `s` key cycles 2, 4, 8, default 4),
+ * guided-filtered there with a (2*(8/s)+1)^2 box and the coefficient means are bilinearly up-sampled.  In place,
+ * asynchronous.  Results equal oracle/stereo_oracle.c::orc_cost_filter_fgf bit for bit, which is pinned against
+ * OpenCV's own (non-IPP) cv::blur / cv::resize arithmetic (tests/golden/make_golden_fgf.py). */
+int psm_cost_filter_fgf(psm_ctx* ctx, int sub_sample_rate);
 
 /* Stage 3: WTA over d in [1, max_disp) for both views; copies the u8 maps to HOST memory
  * (row steps in bytes) and synchronises (DispSelect_GPU).  Only valid on an unsharded context. */

@@ -47,6 +47,8 @@ def lib():
         L.orc_disp_select.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _u8p, _u8p]
         L.orc_pipeline.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    _f32p, _f32p, _u8p, _u8p, _f64p]
+        L.orc_cost_filter_fgf.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p]
+        L.orc_cost_filter_fgf.restype = C.c_int
         L.orc_wmf.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, _u8p]
         L.orc_f32_to_u8x255.argtypes = [_f32p, _u8p, C.c_size_t]
         for name in ("orc_cost_const", "orc_cost_filter", "orc_disp_select", "orc_pipeline"):
@@ -190,3 +192,13 @@ def post_process(img3_f32, disp, r=9):
     out = np.empty((H, W), np.uint8)
     lib().orc_wmf(disp, img8, W, H, r, out)
     return out
+
+
+def cost_filter_fgf(l, r, lv, rv, s=4, threads=8):
+    """DispEst::CostFilter_FGF (Fast Guided Filter, sub-sampling rate s) on copies of the volumes -> lVolF, rVolF"""
+    l, r = _c(l), _c(r)
+    lv, rv = _c(lv).copy(), _c(rv).copy()
+    D, H, W = lv.shape
+    rc = lib().orc_cost_filter_fgf(l, r, W, H, D, threads, s, lv, rv)
+    assert rc == 0
+    return lv, rv

@@ -525,3 +525,189 @@ void orc_f32_to_u8x255(const float* src, uint8_t* dst, size_t n)
         dst[i] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
     }
 }
+
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fast Guided Filter branch: FastGuidedFilterColor (src/fastguidedfilter.cpp:121-198) as driven by
+ * DispEst::CostFilter_FGF (src/DispEst.cpp:281-296): FastGuidedFilter(img, GIF_R_WIN, GIF_EPS, s) -> box size
+ * K = 2*(8/s)+1 on the s-times sub-sampled planes (:206-208).
+ * OpenCV primitives restated from OpenCV's own implementation and pinned against cv2 4.13 (IPP off) by
+ * tests/golden/make_golden_fgf.py: cv::blur == normalised K x K box, anchor K/2, BORDER_REFLECT_101, double
+ * accumulation, * (1.0/(K*K)) in double, one rounding; cv::resize INTER_NN: x -> min(floor(x * (1/(w2/W))), W-1);
+ * cv::resize INTER_LINEAR: f = (float)((d+0.5)*(sn/dn) - 0.5), i = floor(f), f -= i; horizontally the border clamps
+ * with f = 0, vertically the two row indices clamp and f is kept; out = S0*(1-f) + S1*f in float, rows after columns.
+ * cv::MatExpr lowering (matop.cpp): a.mul(b) is a rounded product; X - Y + eps -> addWeighted == (X - Y + eps) in DOUBLE, one rounding;
+ * /= is a true division.  PARITY NOTE: with IPP, cv::resize INTER_LINEAR differs by up to 1e-4 (build-dependent).
+ * -------------------------------------------------------------------------------------------------------------- */
+void orc_box_k(const float* src, int W, int H, int K, float* dst)
+{
+    const int a = K / 2;
+    const double scale = 1.0 / ((double)K * K);
+    double* rows = (double*)malloc((size_t)W * H * sizeof(double));
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            double sacc = 0.0;
+            for (int dx = -a; dx < K - a; ++dx) sacc += (double)src[(size_t)y * W + reflect101(x + dx, W)];
+            rows[(size_t)y * W + x] = sacc;
+        }
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            double sacc = 0.0;
+            for (int dy = -a; dy < K - a; ++dy) sacc += rows[(size_t)reflect101(y + dy, H) * W + x];
+            dst[(size_t)y * W + x] = (float)(sacc * scale);
+        }
+    free(rows);
+}
+
+typedef struct {
+    int W, H, w2, h2, s, K;
+    float* orig[3];   /* full-resolution channels (split) */
+    float* Ic[3];     /* sub-sampled channels */
+    float* m[3];      /* box means of Ic */
+    float* inv[6];    /* rr rg rb gg gb bb of (Sigma + eps I)^-1 */
+    int *xs, *ys;     /* NN source indices */
+    int *lx0, *lx1, *ly0, *ly1; float *fx, *fy;   /* bilinear up-sampling plan */
+} fgf_guide;
+
+static float* fnew(size_t n) { return (float*)malloc(n * sizeof(float)); }
+
+static void fgf_free(fgf_guide* g)
+{
+    for (int k = 0; k < 3; ++k) { free(g->orig[k]); free(g->Ic[k]); free(g->m[k]); }
+    for (int k = 0; k < 6; ++k) free(g->inv[k]);
+    free(g->xs); free(g->ys); free(g->lx0); free(g->lx1); free(g->ly0); free(g->ly1); free(g->fx); free(g->fy);
+}
+
+static void fgf_build(fgf_guide* g, const float* img3, int W, int H, int s, float eps)
+{
+    memset(g, 0, sizeof(*g));
+    g->W = W; g->H = H; g->s = s; g->w2 = W / s; g->h2 = H / s; g->K = 2 * (ORC_GIF_R_WIN / s) + 1;
+    const int w2 = g->w2, h2 = g->h2, K = g->K;
+    const size_t n = (size_t)W * H, n2 = (size_t)w2 * h2;
+    g->xs = (int*)malloc(w2 * sizeof(int)); g->ys = (int*)malloc(h2 * sizeof(int));
+    { const double ifx = 1.0 / ((double)w2 / W), ify = 1.0 / ((double)h2 / H);
+      for (int x = 0; x < w2; ++x) { int v = (int)floor(x * ifx); g->xs[x] = v < W - 1 ? v : W - 1; }
+      for (int y = 0; y < h2; ++y) { int v = (int)floor(y * ify); g->ys[y] = v < H - 1 ? v : H - 1; } }
+    g->lx0 = (int*)malloc(W * sizeof(int)); g->lx1 = (int*)malloc(W * sizeof(int)); g->fx = fnew(W);
+    g->ly0 = (int*)malloc(H * sizeof(int)); g->ly1 = (int*)malloc(H * sizeof(int)); g->fy = fnew(H);
+    { const double sc = (double)w2 / W;
+      for (int x = 0; x < W; ++x) {
+          float f = (float)((x + 0.5) * sc - 0.5); int i = (int)floorf(f); f -= (float)i;
+          if (i < 0) { f = 0.f; i = 0; }
+          if (i >= w2 - 1) { f = 0.f; i = w2 - 1; }
+          g->lx0[x] = i; g->lx1[x] = i + 1 < w2 ? i + 1 : w2 - 1; g->fx[x] = f; } }
+    { const double sc = (double)h2 / H;
+      for (int y = 0; y < H; ++y) {
+          float f = (float)((y + 0.5) * sc - 0.5); int i = (int)floorf(f); f -= (float)i;
+          int i0 = i < 0 ? 0 : (i > h2 - 1 ? h2 - 1 : i), i1 = i + 1 < 0 ? 0 : (i + 1 > h2 - 1 ? h2 - 1 : i + 1);
+          g->ly0[y] = i0; g->ly1[y] = i1; g->fy[y] = f; } }
+    for (int k = 0; k < 3; ++k) {
+        g->orig[k] = fnew(n); g->Ic[k] = fnew(n2); g->m[k] = fnew(n2);
+        for (size_t i = 0; i < n; ++i) g->orig[k][i] = img3[3 * i + k];
+        for (int y = 0; y < h2; ++y) for (int x = 0; x < w2; ++x) g->Ic[k][(size_t)y * w2 + x] = g->orig[k][(size_t)g->ys[y] * W + g->xs[x]];
+        orc_box_k(g->Ic[k], w2, h2, K, g->m[k]);
+    }
+    float* var[6]; float* t = fnew(n2);
+    static const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {0, 1, 2, 1, 2, 2};
+    for (int v = 0; v < 6; ++v) {
+        var[v] = fnew(n2);
+        for (size_t i = 0; i < n2; ++i) t[i] = g->Ic[pa[v]][i] * g->Ic[pb[v]][i];
+        orc_box_k(t, w2, h2, K, var[v]);
+        const int diag = pa[v] == pb[v];
+        for (size_t i = 0; i < n2; ++i) {
+            const float mm = g->m[pa[v]][i] * g->m[pb[v]][i];
+            /* fastguidedfilter.cpp:144-149: 'box - m.mul(m) + eps' lowers to addWeighted(box, 1, mm, -1, eps), which
+               evaluates in double and rounds once; the off-diagonal terms are a plain float subtract */
+            var[v][i] = diag ? (float)(((double)var[v][i] - (double)mm) + (double)eps) : var[v][i] - mm;
+        }
+    }
+    float *rr = var[0], *rg = var[1], *rb = var[2], *gg = var[3], *gb = var[4], *bb = var[5];
+    for (int k = 0; k < 6; ++k) g->inv[k] = fnew(n2);
+    for (size_t i = 0; i < n2; ++i) {                                         /* :152-166 */
+        const float irr = gg[i] * bb[i] - gb[i] * gb[i];
+        const float irg = gb[i] * rb[i] - rg[i] * bb[i];
+        const float irb = rg[i] * gb[i] - gg[i] * rb[i];
+        const float igg = rr[i] * bb[i] - rb[i] * rb[i];
+        const float igb = rb[i] * rg[i] - rr[i] * gb[i];
+        const float ibb = rr[i] * gg[i] - rg[i] * rg[i];
+        const float det = (irr * rr[i] + irg * rg[i]) + irb * rb[i];
+        g->inv[0][i] = irr / det; g->inv[1][i] = irg / det; g->inv[2][i] = irb / det;
+        g->inv[3][i] = igg / det; g->inv[4][i] = igb / det; g->inv[5][i] = ibb / det;
+    }
+    for (int v = 0; v < 6; ++v) free(var[v]);
+    free(t);
+}
+
+static void fgf_upsample(const fgf_guide* g, const float* lo, float* full, float* tmp /* h2 x W */)
+{
+    const int W = g->W, H = g->H, w2 = g->w2, h2 = g->h2;
+    for (int y = 0; y < h2; ++y)
+        for (int x = 0; x < W; ++x)
+            tmp[(size_t)y * W + x] = lo[(size_t)y * w2 + g->lx0[x]] * (1.f - g->fx[x]) + lo[(size_t)y * w2 + g->lx1[x]] * g->fx[x];
+    for (int y = 0; y < H; ++y) {
+        const float b0 = 1.f - g->fy[y], b1 = g->fy[y];
+        const float *r0 = tmp + (size_t)g->ly0[y] * W, *r1 = tmp + (size_t)g->ly1[y] * W;
+        for (int x = 0; x < W; ++x) full[(size_t)y * W + x] = r0[x] * b0 + r1[x] * b1;
+    }
+}
+
+static void fgf_filter(const fgf_guide* g, float* p /* in place, full resolution */)
+{
+    const int W = g->W, H = g->H, w2 = g->w2, h2 = g->h2, K = g->K;
+    const size_t n = (size_t)W * H, n2 = (size_t)w2 * h2;
+    float *p2 = fnew(n2), *mp = fnew(n2), *t = fnew(n2), *mIp[3], *a[3], *b = fnew(n2), *tmp = fnew((size_t)h2 * W), *up = fnew(n), *q = fnew(n);
+    for (int y = 0; y < h2; ++y) for (int x = 0; x < w2; ++x) p2[(size_t)y * w2 + x] = p[(size_t)g->ys[y] * W + g->xs[x]];
+    orc_box_k(p2, w2, h2, K, mp);
+    for (int k = 0; k < 3; ++k) {
+        mIp[k] = fnew(n2); a[k] = fnew(n2);
+        for (size_t i = 0; i < n2; ++i) t[i] = g->Ic[k][i] * p2[i];
+        orc_box_k(t, w2, h2, K, mIp[k]);
+    }
+    for (size_t i = 0; i < n2; ++i) {
+        const float c0 = mIp[0][i] - g->m[0][i] * mp[i], c1 = mIp[1][i] - g->m[1][i] * mp[i], c2 = mIp[2][i] - g->m[2][i] * mp[i];   /* :178-180 */
+        const float ar = (g->inv[0][i] * c0 + g->inv[1][i] * c1) + g->inv[2][i] * c2;      /* :182-184 */
+        const float ag = (g->inv[1][i] * c0 + g->inv[3][i] * c1) + g->inv[4][i] * c2;
+        const float ab = (g->inv[2][i] * c0 + g->inv[4][i] * c1) + g->inv[5][i] * c2;
+        a[0][i] = ar; a[1][i] = ag; a[2][i] = ab;
+        b[i] = ((mp[i] - ar * g->m[0][i]) - ag * g->m[1][i]) - ab * g->m[2][i];             /* :186 */
+    }
+    for (int k = 0; k < 3; ++k) {
+        orc_box_k(a[k], w2, h2, K, t);
+        fgf_upsample(g, t, up, tmp);
+        for (size_t i = 0; i < n; ++i) {
+            const float prod = up[i] * g->orig[k][i];
+            q[i] = k == 0 ? prod : q[i] + prod;                                              /* :196 (t1 + t2) + t3 */
+        }
+    }
+    orc_box_k(b, w2, h2, K, t);
+    fgf_upsample(g, t, up, tmp);
+    for (size_t i = 0; i < n; ++i) p[i] = q[i] + up[i];
+    for (int k = 0; k < 3; ++k) { free(mIp[k]); free(a[k]); }
+    free(p2); free(mp); free(t); free(b); free(tmp); free(up); free(q);
+}
+
+typedef struct { const fgf_guide* g; float* slice; } fgf_task;
+static void* fgf_thread(void* arg) { fgf_task* k = (fgf_task*)arg; fgf_filter(k->g, k->slice); return NULL; }
+
+/* DispEst::CostFilter_FGF (DispEst.cpp:281-296; OpenMP over d there, `threads` pthreads here), volumes filtered in place */
+int orc_cost_filter_fgf(const float* lImg, const float* rImg, int W, int H, int D, int threads, int s, float* lVol, float* rVol)
+{
+    if (s < 1 || W / s < 1 || H / s < 1) return -1;
+    const float* imgs[2] = {lImg, rImg};
+    float* vols[2] = {lVol, rVol};
+    if (threads < 1) threads = 1;
+    for (int v = 0; v < 2; ++v) {
+        fgf_guide g;
+        fgf_build(&g, imgs[v], W, H, s, ORC_GIF_EPS);
+        pthread_t* th = (pthread_t*)malloc((size_t)D * sizeof(pthread_t));
+        fgf_task* tk = (fgf_task*)malloc((size_t)D * sizeof(fgf_task));
+        for (int d0 = 0; d0 < D; d0 += threads) {
+            const int nb = d0 + threads <= D ? threads : D - d0;
+            for (int i = 0; i < nb; ++i) { tk[d0 + i].g = &g; tk[d0 + i].slice = vols[v] + (size_t)(d0 + i) * W * H; pthread_create(&th[d0 + i], NULL, fgf_thread, &tk[d0 + i]); }
+            for (int i = 0; i < nb; ++i) pthread_join(th[d0 + i], NULL);
+        }
+        free(th); free(tk);
+        fgf_free(&g);
+    }
+    return 0;
+}

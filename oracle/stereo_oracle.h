@@ -91,6 +91,11 @@ int orc_pipeline(const float* lImg, const float* rImg, int W, int H, int D, int 
                  int gray_mode, float* lVol, float* rVol, uint8_t* lDis, uint8_t* rDis,
                  double* times_ms);
 
+/* Fast Guided Filter branch (src/fastguidedfilter.cpp via DispEst::CostFilter_FGF, DispEst.cpp:281-296), s = sub-sampling
+ * rate (2, 4, 8), volumes filtered in place.  Pinned against cv2 (IPP off) by tests/golden/make_golden_fgf.py. */
+void orc_box_k(const float* src, int W, int H, int K, float* dst);
+int orc_cost_filter_fgf(const float* lImg, const float* rImg, int W, int H, int D, int threads, int s, float* lVol, float* rVol);
+
 /* Post-processing (PP::processDM live code, src/PP.cpp:414-422 -> JointWMF::filter): see stereo_oracle.c.
  * PARITY UNPINNED for natural images (cv::kmeans feature clustering is RNG-seeded); this is the un-clustered filter. */
 void orc_pp_weight_lut(uint32_t* lut /* 3*63*63 + 1 entries, 2^-22 fixed point */);

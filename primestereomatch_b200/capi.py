@@ -16,7 +16,7 @@ SYMBOLS = [
     "psm_set_stream", "psm_set_images", "psm_set_images_u8", "psm_set_images_device",
     "psm_set_images_async", "psm_set_images_u8_async", "psm_set_images_commit", "psm_disp_select_async",
     "psm_cost_const", "psm_cost_filter", "psm_disp_select", "psm_disp_select_device",
-    "psm_post_process", "psm_post_process_device", "psm_disp_select_keys", "psm_disp_reduce_keys", "psm_p2p_create_buffer", "psm_ipc_export", "psm_ipc_import",
+    "psm_post_process", "psm_post_process_device", "psm_cost_filter_fgf", "psm_disp_select_keys", "psm_disp_reduce_keys", "psm_p2p_create_buffer", "psm_ipc_export", "psm_ipc_import",
     "psm_p2p_set_peers", "psm_disp_select_keys_p2p", "psm_disp_reduce_p2p", "psm_disp_fetch_p2p", "psm_read_cost_slice", "psm_write_cost_slice",
     "psm_read_guide_plane", "psm_read_ab_slice", "psm_device_ptr", "psm_stage_ms",
     "psm_launch_count", "psm_sync", "psm_last_error", "psm_build_info",
@@ -60,6 +60,7 @@ def lib():
     L.psm_set_images_u8_async.argtypes = [vp, u8p, sz, u8p, sz]
     L.psm_set_images_commit.argtypes = [vp]
     L.psm_disp_select_async.argtypes = [vp, u8p, sz, u8p, sz]
+    L.psm_cost_filter_fgf.argtypes = [vp, i]
     L.psm_post_process.argtypes = [vp, u8p, sz, u8p, sz]
     L.psm_post_process_device.argtypes = [vp]
     L.psm_cost_const.argtypes = [vp]

@@ -123,6 +123,13 @@ class DispEst:
         capi.check(self._lib.psm_cost_filter(self._ctx), self._ctx)
         return 0
 
+    def CostFilter_FGF_GPU(self):
+        """Device twin of DispEst::CostFilter_FGF (DispEst.cpp:281-296): Fast Guided Filter at the sub-sampling rate
+        set by setSubsampleRate (default 4, like StereoMatch.cpp:33)."""
+        self._need_gpu()
+        capi.check(self._lib.psm_cost_filter_fgf(self._ctx, int(self.subsample_rate)), self._ctx)
+        return 0
+
     def DispSelect_GPU(self):
         """DispEst.cpp:323-328: WTA, results land in lDisMap / rDisMap."""
         self._need_gpu()
