@@ -233,7 +233,10 @@ int launch_cvf_stream(psm_ctx* c)
     for (int v = 0; v < 2; ++v) { P.vol_in[v] = c->vol[v]; P.vol_out[v] = c->vol_alt[v]; P.guide[v] = c->guide[v]; }
     P.W = c->W; P.H = c->H; P.Wp = c->Wp; P.Dloc = c->d_count;
     P.nstrips = (c->W + kStripOut - 1) / kStripOut;
-    const int nthreads = c->cvf_threads > 0 ? c->cvf_threads : kCvfThreads;
+    // slice-warps per CTA: 3 (4 CTAs per SM) or 4 (3 CTAs per SM) -- the same 12 warps per SM either way; take the one that
+    // leaves no warp slot idle in the last slice group (16 slices per rank at 8 GPUs: 4 x 4 instead of 6 x 3 with two idle)
+    const int auto_threads = (c->d_count % 3 != 0 && c->d_count % 4 == 0) ? 128 : kCvfThreads;
+    const int nthreads = c->cvf_threads > 0 ? c->cvf_threads : auto_threads;
     const int wpc = nthreads / 32;
     P.ndgroups = (c->d_count + wpc - 1) / wpc;
     // enough CTAs for several waves over 148 SMs x 3 resident CTAs, but segments no shorter than

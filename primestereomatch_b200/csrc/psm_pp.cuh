@@ -15,8 +15,8 @@
 // by the reference itself; this kernel needs no clustering -- it evaluates the weights directly.
 //
 // B200 mapping (nothing like the reference's serial column scan with necklace tables): one WARP per pixel,
-//   lanes 0..18 = the 19 window columns, 19 rounds = the window rows (coalesced 76-byte row reads of a packed
-//   u32 image: disparity << 24 | R6 << 16 | G6 << 8 | B6);
+//   the 361 window taps dealt round-robin to the 32 lanes (12 rounds), each tap one 4-byte load of a packed
+//   u32 image (disparity << 24 | R6 << 16 | G6 << 8 | B6);
 //   per round the lanes holding the same disparity combine their weights (ballot + __reduce_add_sync) and one
 //   lane adds the sum to a 256-bin histogram in shared memory (1 KB per warp): integer sums, order-independent;
 //   then each lane scans 8 bins, a warp prefix sum finds the first bin where 2*cum >= total.
@@ -61,14 +61,17 @@ __global__ void __launch_bounds__(kPpWarps * 32) pp_wmf_kernel(const uint32_t* _
         const int y = (int)(pix / W), x = (int)(pix - (long)y * W);
         const uint32_t cp = __ldg(packed + pix);
         const int pb = cp & 63, pg = (cp >> 8) & 63, pr = (cp >> 16) & 63;
-        const int xx = x - kPpRadius + lane;
-        const bool col_ok = lane <= 2 * kPpRadius && xx >= 0 && xx < W;
-        const int y0 = max(0, y - kPpRadius), y1 = min(H - 1, y + kPpRadius);
         uint32_t total = 0;
-        for (int yy = y0; yy <= y1; ++yy) {
+        constexpr int kSide = 2 * kPpRadius + 1, kTaps = kSide * kSide;
+        // the 361 window taps are dealt to the 32 lanes round-robin (12 rounds); a lane's tap is (i / 19, i % 19)
+        for (int base = 0; base < kTaps; base += 32) {
+            const int i = base + lane;
+            const int dy = i / kSide, dx = i - dy * kSide;
+            const int yy = y - kPpRadius + dy, xx = x - kPpRadius + dx;
+            const bool ok = i < kTaps && yy >= 0 && yy < H && xx >= 0 && xx < W;
             uint32_t w = 0;
             unsigned dq = 0x100u + lane;      // a key no valid tap has
-            if (col_ok) {
+            if (ok) {
                 const uint32_t cq = __ldg(packed + (size_t)yy * W + xx);
                 const int d0 = pb - (int)(cq & 63), d1 = pg - (int)((cq >> 8) & 63), d2 = pr - (int)((cq >> 16) & 63);
                 w = __ldg(lut + (d0 * d0 + d1 * d1 + d2 * d2));
@@ -76,12 +79,12 @@ __global__ void __launch_bounds__(kPpWarps * 32) pp_wmf_kernel(const uint32_t* _
             }
             total += w;
             // combine the taps that carry the same disparity (neighbouring pixels usually do) before touching shared memory
-            unsigned todo = __ballot_sync(0xffffffffu, col_ok);
+            unsigned todo = __ballot_sync(0xffffffffu, ok);
             while (todo) {
                 const int leader = __ffs(todo) - 1;
                 const unsigned v = __shfl_sync(0xffffffffu, dq, leader);
-                const unsigned same = __ballot_sync(0xffffffffu, col_ok && dq == v);
-                if (col_ok && dq == v) {
+                const unsigned same = __ballot_sync(0xffffffffu, ok && dq == v);
+                if (ok && dq == v) {
                     const uint32_t s = __reduce_add_sync(same, w);
                     if (lane == leader) h[v] += s;
                 }
