@@ -131,7 +131,7 @@ int psm_cost_filter(psm_ctx* ctx);
 /* Stage 2, Fast-Guided-Filter variant (DispEst::CostFilter_FGF, what the reference's CPU branch runs today): every
  * slice is sub-sampled by `sub_sample_rate` (1, 2, 4 or 8; the reference's `s` key cycles 2, 4, 8, default 4),
  * guided-filtered there with a (2*(8/s)+1)^2 box and the coefficient means are bilinearly up-sampled.  In place,
- * asynchronous.  Results equal oracle/stereo_oracle.c::orc_cost_filter_fgf bit for bit, which is pinned against
+ * asynchronous.  Results equal the CPU restatement orc_cost_filter_fgf (test infrastructure, oracle/) bit for bit, which is pinned against
  * OpenCV's own (non-IPP) cv::blur / cv::resize arithmetic (tests/golden/make_golden_fgf.py). */
 int psm_cost_filter_fgf(psm_ctx* ctx, int sub_sample_rate);
 

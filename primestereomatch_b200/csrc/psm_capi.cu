@@ -614,7 +614,7 @@ int psm_cost_filter_fgf(psm_ctx* c, int s)
         PSM_CUDA(c, cudaMalloc(&c->fgf_mean, (size_t)4 * c->d_count * n2 * sizeof(float)));
         PSM_CUDA(c, cudaMalloc(&c->fgf_plan_i, (size_t)2 * (c->W + c->H) * sizeof(int)));
         PSM_CUDA(c, cudaMalloc(&c->fgf_plan_f, (size_t)(c->W + c->H) * sizeof(float)));
-        // cv::resize INTER_LINEAR coordinates (OpenCV's own implementation; see oracle/stereo_oracle.c fgf_build)
+        // cv::resize INTER_LINEAR coordinates (OpenCV's own implementation; same expressions as the CPU restatement fgf_build in oracle/)
         int* hi = new (std::nothrow) int[2 * (c->W + c->H)];
         float* hf = new (std::nothrow) float[c->W + c->H];
         if (!hi || !hf) { delete[] hi; delete[] hf; return fail(c, PSM_ENOMEM, "out of host memory"); }

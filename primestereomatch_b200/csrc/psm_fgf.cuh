@@ -6,7 +6,7 @@
 // coefficient means are bilinearly up-sampled and applied at full resolution.  It is what the reference's CPU
 // branch runs today (src/StereoMatch.cpp:214); it is NOT the full-resolution GIF of psm_cvf_stream.cuh.
 //
-// Numerics follow oracle/stereo_oracle.c::orc_fgf_* (pinned against cv2 with IPP off, tests/golden/
+// Numerics follow the CPU restatement orc_fgf_* (test infrastructure, oracle/) (pinned against cv2 with IPP off, tests/golden/
 // make_golden_fgf.py): box sums in fp64 (exact: <= 81 terms), * 1/(K*K) in double, one rounding; every float
 // operation a separate IEEE op in source order; the diagonal variance terms (x - y + eps) in double with one
 // rounding (cv::addWeighted); true divisions; OpenCV's own INTER_NN / INTER_LINEAR index and weight formulas

@@ -5,7 +5,7 @@
 // (vendored include/JointWMF.h:81-155, filterCore :173-390) and which the reference runs on the CPU even in
 // its GPU mode (src/DispEst.cpp:338-344).
 //
-// What is computed (exactly what oracle/stereo_oracle.c::orc_wmf restates, and what the reference's
+// What is computed (exactly what the CPU restatement orc_wmf (test infrastructure, oracle/) restates, and what the reference's
 // JointWMF computes whenever the feature image has <= 256 distinct 6-bit colours): for every pixel p
 //   out(p) = min { v : sum_{q in window, I_q <= v} w(p,q)  >=  sum_{q in window, I_q > v} w(p,q) }
 // window = (2r+1)^2 clipped at the image border, w = exp(-|c_p - c_q|^2 / (2 s^2)) on the 6-bit colours
