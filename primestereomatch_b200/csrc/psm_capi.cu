@@ -273,6 +273,8 @@ int launch_cvf_stream(psm_ctx* c)
         case 7: kern = cvf_stream_kernel<5, 1, kS2Mixed, 1, 0>; break;   // 144 registers
         case 8: kern = cvf_stream_kernel<6, 1, kS2Mixed, 1, 0>; break;   // 152 registers
         case 9: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1, 2>; staged = true; break;   // TMA-staged guide rows
+        case 10: kern = cvf_stream_kernel<4, 1, kS2Mixed, 1, 3>; break;  // light prefetch, <= 128 registers: 16 warps per SM with 128-thread CTAs
+        case 11: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1, 3>; break;  // light prefetch, 168 registers
         default: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1>; break;
         }
     } else {
@@ -285,6 +287,8 @@ int launch_cvf_stream(psm_ctx* c)
         case 7: kern = cvf_stream_kernel<3, 2, kS2Exact, 1, 1>; break;
         case 8: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 0>; break;
         case 9: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 2>; staged = true; break;   // TMA-staged guide rows
+        case 10: kern = cvf_stream_kernel<4, 1, kS2Exact, 1, 3>; break;  // light prefetch, <= 128 registers
+        case 11: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 3>; break;  // light prefetch, 168 registers
         default: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 1>; break;
         }
     }

@@ -239,7 +239,8 @@ __device__ __forceinline__ float4 lds4(unsigned addr)
 // S2M : kS2Exact / kS2Mixed
 // TM  : 1 = history ring in tensor memory (tcgen05.ld/st), 0 = in shared memory
 // PF  : 1 = prefetch the next step's guide rows into L1;  2 = stage the guide rows in shared memory with bulk async
-//       copies (TMA) issued two steps ahead by one lane per CTA (needs TM = 1: the ring is not in shared memory)
+//       copies (TMA) issued two steps ahead by one lane per CTA (needs TM = 1: the ring is not in shared memory);
+//       3 = light prefetch (only the newest p row a step ahead; everything else is an L1 hit with the ring in TMEM)
 // register budgets by MINB: 3 -> 168 regs (3 CTAs x 128 thr or 4 x 96: 12 warps/SM); 4 -> 128 regs (16 warps);
 // 5 -> 144 regs (2 CTAs x 224 thr = 14 warps, two TMEM column blocks per lane quarter); 6 -> 152 regs (13 warps)
 constexpr int cvf_max_regs(int minb) { return minb == 3 ? 168 : (minb == 4 ? 128 : (minb == 5 ? 144 : 152)); }
@@ -677,7 +678,72 @@ cvf_stream_kernel(const CvfParams P)
             }
             ro_y += rowB;
         };
-        if (!ST) {
+        if (PF == 3) {
+            // ---- "light prefetch" steady loop: with the ring in tensor memory the whole shared-memory array is L1, so
+            // only the NEWEST p row (which comes from HBM) is loaded a step ahead; the image rows, the oldest p row
+            // (read 7 steps ago by this warp) and the coefficient rows are L1 hits and are loaded where they are used.
+            // 28 fewer live registers than the full prefetch: the build for 16 warps per SM (<= 128 registers).
+            float4 pn = xn.p;
+            auto steady_lp = [&](auto slow_tag) {
+                constexpr bool SLOW = decltype(slow_tag)::value;
+                f2x2 av[4];
+                {
+                    float4 g4[10];
+                    load_guide(ro_t, g4);
+                    RowIn x;
+                    x.p = pn; x.i0 = ldg4(Gi + ro_n); x.i1 = ldg4(Gi + (planeB + ro_n)); x.i2 = ldg4(Gi + (2 * planeB + ro_n));
+                    add_row(x, SLOW);
+                    ro_n += rowB;
+                    pn = ldg4(vin + ro_n);
+                    coeffs(g4, av);
+                    const RowIn xold = load_at(ro_o);
+                    sub_row(xold, SLOW);
+                    ro_o += rowB;
+                    ro_t += rowB;
+                }
+                const float4 o0 = ldg4(Go + ro_y), o1 = ldg4(Go + (planeB + ro_y)), o2 = ldg4(Go + (2 * planeB + ro_y));
+                if (!MIXED) {
+                    f2x2 old[4];
+                    ring_wait_st();
+                    ring_ld(t & 7, old);
+                    ring_wait_ld();
+                    ring_st(t & 7, av);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            S2[MIXED ? 0 : q][j] = __dsub_rn(__dadd_rn(S2[MIXED ? 0 : q][j], w2(get(av[q], j), SLOW)), w2(get(old[q], j), SLOW));
+                    }
+                    emit(ro_y, o0, o1, o2);
+                } else {
+                    f2x2 pa[4], pb[4], pc[4], pd[4];
+                    ring_wait_st();
+                    ring_ld((t - 6) & 7, pa);
+                    ring_ld((t - 4) & 7, pb);
+                    ring_wait_ld();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pa[q] = addp(pa[q], pb[q]);
+                    ring_ld((t - 2) & 7, pc);
+                    ring_ld(t & 7, pd);
+                    ring_wait_ld();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pd[q] = add2(av[q], pd[q]);
+                    ring_st(t & 7, pd);
+                    ring_st((t + 1) & 7, av);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pc[q] = addp(pc[q], pd[q]);
+                    emit_pairs(ro_y, pa, pc, o0, o1, o2);
+                }
+                ro_y += rowB;
+            };
+            if (IW) {
+                for (; t <= Ts1 && !slow; ++t) {
+                    if (needs_slow(pn, pn)) { slow = true; break; }   // the oldest row was checked when it was the newest
+                    steady_lp(std::false_type{});
+                }
+            }
+            for (; t <= Ts1; ++t) steady_lp(std::true_type{});
+        } else if (!ST) {
             if (IW) {
                 for (; t <= Ts1 && !slow; ++t) {
                     if (needs_slow(xn.p, xo.p)) { slow = true; break; }
