@@ -275,6 +275,8 @@ int launch_cvf_stream(psm_ctx* c)
         case 9: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1, 2>; staged = true; break;   // TMA-staged guide rows
         case 10: kern = cvf_stream_kernel<4, 1, kS2Mixed, 1, 3>; break;  // light prefetch, <= 128 registers: 16 warps per SM with 128-thread CTAs
         case 11: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1, 3>; break;  // light prefetch, 168 registers
+        case 12: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1, 0, 1>; break;  // packed exact adds
+        case 13: kern = cvf_stream_kernel<4, 1, kS2Mixed, 1, 3, 1>; break;  // packed exact adds + light prefetch, 128 registers
         default: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1>; break;
         }
     } else {
@@ -289,6 +291,7 @@ int launch_cvf_stream(psm_ctx* c)
         case 9: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 2>; staged = true; break;   // TMA-staged guide rows
         case 10: kern = cvf_stream_kernel<4, 1, kS2Exact, 1, 3>; break;  // light prefetch, <= 128 registers
         case 11: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 3>; break;  // light prefetch, 168 registers
+        case 12: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 1, 1>; break;  // packed exact adds
         default: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 1>; break;
         }
     }
@@ -297,6 +300,7 @@ int launch_cvf_stream(psm_ctx* c)
     if (tm && !staged && !c->cvf_extra_smem)  // nothing lives in shared memory: give the whole array to L1 (the guide rows are re-read by every slice)
         PSM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
     P.guide_flags = c->guide_flags;
+    P.one = 1.0f; P.mone = -1.0f;
     const unsigned grid = 2u * P.nseg * P.nstrips * P.ndgroups;
     kern<<<grid, nthreads, smem, c->stream>>>(P);
     PSM_LAUNCH_CHECK(c);

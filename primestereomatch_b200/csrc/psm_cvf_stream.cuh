@@ -87,6 +87,7 @@ struct CvfParams {
     int W, H, Wp, Dloc;
     int nstrips, nseg, seg_rows, ndgroups;
     int remap_sms, remap_ctas;  // SM count and resident CTAs per SM for the block->work remap (0: identity)
+    float one, mone;            // +1.0f / -1.0f, passed at run time so that the compiler cannot fold them (packed exact adds, PA)
 };
 
 struct f2x2 { float2 lo, hi; };  // four columns as two packed pairs
@@ -101,6 +102,18 @@ __device__ __forceinline__ f2x2 sub2(const f2x2& a, const f2x2& b)
 {
     return {make_float2(fsub(a.lo.x, b.lo.x), fsub(a.lo.y, b.lo.y)), make_float2(fsub(a.hi.x, b.hi.x), fsub(a.hi.y, b.hi.y))};
 }
+// Packed EXACT add / subtract of values that may be products: x + y == fma(x, 1, y) and x - y == fma(y, -1, x) with one
+// rounding each, so an FFMA2 whose multiplier is a RUN-TIME 1.0f / -1.0f (ptxas cannot fold or re-associate it, and an fma
+// is never contracted with the multiply that feeds it) does two IEEE additions per instruction.  This sidesteps the
+// FMUL2 + FADD2 -> FFMA2 contraction of ptxas 12.9 that forces plain adds of products to stay scalar.
+__device__ __forceinline__ float2 fma2(const float2& a, const float2& b, const float2& c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&b)), "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
 // packed add (FADD2): only for operands that are NOT products (see the contraction note above)
 __device__ __forceinline__ f2x2 addp(const f2x2& a, const f2x2& b) { return {__fadd2_rn(a.lo, b.lo), __fadd2_rn(a.hi, b.hi)}; }
 __device__ __forceinline__ float get(const f2x2& v, int j) { return j == 0 ? v.lo.x : (j == 1 ? v.lo.y : (j == 2 ? v.hi.x : v.hi.y)); }
@@ -238,6 +251,7 @@ __device__ __forceinline__ float4 lds4(unsigned addr)
 //       stage 1 (non-negative values: one instruction each), F2F in the exact stage 2 (signed values would cost three)
 // S2M : kS2Exact / kS2Mixed
 // TM  : 1 = history ring in tensor memory (tcgen05.ld/st), 0 = in shared memory
+// PA  : 1 = adds / subtracts of products as packed FFMA2 with a run-time unit multiplier (exact, see fma2)
 // PF  : 1 = prefetch the next step's guide rows into L1;  2 = stage the guide rows in shared memory with bulk async
 //       copies (TMA) issued two steps ahead by one lane per CTA (needs TM = 1: the ring is not in shared memory);
 //       3 = light prefetch (only the newest p row a step ahead; everything else is an L1 hit with the ring in TMEM)
@@ -245,7 +259,7 @@ __device__ __forceinline__ float4 lds4(unsigned addr)
 // 5 -> 144 regs (2 CTAs x 224 thr = 14 warps, two TMEM column blocks per lane quarter); 6 -> 152 regs (13 warps)
 constexpr int cvf_max_regs(int minb) { return minb == 3 ? 168 : (minb == 4 ? 128 : (minb == 5 ? 144 : 152)); }
 
-template <int MINB, int IW, int S2M, int TM, int PF = 0>
+template <int MINB, int IW, int S2M, int TM, int PF = 0, int PA = 0>
 __global__ void __maxnreg__(cvf_max_regs(MINB))
 cvf_stream_kernel(const CvfParams P)
 {
@@ -258,6 +272,15 @@ cvf_stream_kernel(const CvfParams P)
     const int lane = tid & 31, warp = tid >> 5;
     const int nthr = blockDim.x;
     const int wpc = nthr >> 5;
+    const float2 kOne2 = make_float2(P.one, P.one), kMone2 = make_float2(P.mone, P.mone);
+    auto xadd = [&](const f2x2& a, const f2x2& b) -> f2x2 {   // a + b, exact, b or a may be products
+        if (PA) return {fma2(a.lo, kOne2, b.lo), fma2(a.hi, kOne2, b.hi)};
+        return add2(a, b);
+    };
+    auto xsub = [&](const f2x2& a, const f2x2& b) -> f2x2 {   // a - b
+        if (PA) return {fma2(b.lo, kMone2, a.lo), fma2(b.hi, kMone2, a.hi)};
+        return sub2(a, b);
+    };
 
     // Block -> work mapping.  Hardware hands consecutive blockIdx to consecutive SMs, so the CTAs that
     // share an SM (and its L1) are blockIdx k, k+nsm, k+2nsm, ...; the remap makes those neighbours in
@@ -450,13 +473,13 @@ cvf_stream_kernel(const CvfParams P)
         const f2x2 M00 = from4(g4[3]), M01 = from4(g4[4]), M02 = from4(g4[5]);
         const f2x2 M11 = from4(g4[6]), M12 = from4(g4[7]), M22 = from4(g4[8]);
         const f2x2 idet = from4(g4[9]);
-        const f2x2 c0 = sub2(m[1], mul2(mI0, m[0]));   // CVF.cpp:92-95
-        const f2x2 c1 = sub2(m[2], mul2(mI1, m[0]));
-        const f2x2 c2 = sub2(m[3], mul2(mI2, m[0]));
-        av[0] = mul2(idet, add2(add2(mul2(c0, M00), mul2(c1, M01)), mul2(c2, M02)));  // CVF.cpp:121-146
-        av[1] = mul2(idet, add2(add2(mul2(c0, M01), mul2(c1, M11)), mul2(c2, M12)));
-        av[2] = mul2(idet, add2(add2(mul2(c0, M02), mul2(c1, M12)), mul2(c2, M22)));
-        av[3] = sub2(sub2(sub2(m[0], mul2(av[0], mI0)), mul2(av[1], mI1)), mul2(av[2], mI2));  // CVF.cpp:152-155
+        const f2x2 c0 = xsub(m[1], mul2(mI0, m[0]));   // CVF.cpp:92-95
+        const f2x2 c1 = xsub(m[2], mul2(mI1, m[0]));
+        const f2x2 c2 = xsub(m[3], mul2(mI2, m[0]));
+        av[0] = mul2(idet, xadd(xadd(mul2(c0, M00), mul2(c1, M01)), mul2(c2, M02)));  // CVF.cpp:121-146
+        av[1] = mul2(idet, xadd(xadd(mul2(c0, M01), mul2(c1, M11)), mul2(c2, M12)));
+        av[2] = mul2(idet, xadd(xadd(mul2(c0, M02), mul2(c1, M12)), mul2(c2, M22)));
+        av[3] = xsub(xsub(xsub(m[0], mul2(av[0], mI0)), mul2(av[1], mI1)), mul2(av[2], mI2));  // CVF.cpp:152-155
         if (fix_left | fix_right) {  // warp-uniform
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -485,9 +508,9 @@ cvf_stream_kernel(const CvfParams P)
 
     // q = box(b) + box(a0)*I0 + box(a1)*I1 + box(a2)*I2, accumulated in that order (CVF.cpp:157-163)
     auto combine = [&](size_t ro, const f2x2 (&mb)[4], const float4& i0, const float4& i1, const float4& i2) {
-        f2x2 qv = add2(mb[3], mul2(mb[0], from4(i0)));
-        qv = add2(qv, mul2(mb[1], from4(i1)));
-        qv = add2(qv, mul2(mb[2], from4(i2)));
+        f2x2 qv = xadd(mb[3], mul2(mb[0], from4(i0)));
+        qv = xadd(qv, mul2(mb[1], from4(i1)));
+        qv = xadd(qv, mul2(mb[2], from4(i2)));
         if (store_ok) *reinterpret_cast<float4*>(vout + ro) = to4(qv);
     };
     // EXACT: stage-2 row sums of S2 -> q for one output row
@@ -566,7 +589,7 @@ cvf_stream_kernel(const CvfParams P)
                 ring_ld(t & 7, pr);
                 ring_wait_ld();
 #pragma unroll
-                for (int q = 0; q < 4; ++q) pr[q] = add2(av[q], pr[q]);
+                for (int q = 0; q < 4; ++q) pr[q] = xadd(av[q], pr[q]);
                 ring_st(t & 7, pr);
             }
             ring_st((t + 1) & 7, av);
@@ -669,7 +692,7 @@ cvf_stream_kernel(const CvfParams P)
                 ring_ld(t & 7, pd);                                              // ab(t-1)
                 ring_wait_ld();
 #pragma unroll
-                for (int q = 0; q < 4; ++q) pd[q] = add2(av[q], pd[q]);          // pair(t): scalar adds (av are products)
+                for (int q = 0; q < 4; ++q) pd[q] = xadd(av[q], pd[q]);          // pair(t): scalar adds (av are products)
                 ring_st(t & 7, pd);
                 ring_st((t + 1) & 7, av);
 #pragma unroll
@@ -727,7 +750,7 @@ cvf_stream_kernel(const CvfParams P)
                     ring_ld(t & 7, pd);
                     ring_wait_ld();
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) pd[q] = add2(av[q], pd[q]);
+                    for (int q = 0; q < 4; ++q) pd[q] = xadd(av[q], pd[q]);
                     ring_st(t & 7, pd);
                     ring_st((t + 1) & 7, av);
 #pragma unroll
@@ -838,7 +861,7 @@ cvf_stream_kernel(const CvfParams P)
                     ring_ld(t & 7, pd);
                     ring_wait_ld();
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) pd[q] = add2(av[q], pd[q]);
+                    for (int q = 0; q < 4; ++q) pd[q] = xadd(av[q], pd[q]);
                     ring_st(t & 7, pd);
                     ring_st((t + 1) & 7, av);
 #pragma unroll
