@@ -47,10 +47,8 @@ struct psm_ctx {
     uint8_t* dis[2] = {nullptr, nullptr};
     // Fast Guided Filter branch (lazy): low-res guide planes per view, low-res coefficient scratch, up-sampling plan
     float* fgf_lo[2] = {nullptr, nullptr};
-    float* fgf_ab = nullptr;
     float* fgf_mean = nullptr;
-    int* fgf_plan_i = nullptr;              // x0[W], x1[W], y0[H], y1[H]
-    float* fgf_plan_f = nullptr;            // fx[W], fy[H]
+    void* fgf_plan = nullptr;               // FgfTap x[W], y[H]: INTER_LINEAR source indices and weights
     int fgf_s = 0;                          // sub-sampling rate the buffers / plan were built for
     uint8_t* dis_pp[2] = {nullptr, nullptr}; // post-processed maps
     uint32_t* pp_packed = nullptr;          // packed (disparity, 6-bit colour) image of one view, lazy
@@ -276,6 +274,8 @@ int launch_cvf_stream(psm_ctx* c)
         case 10: kern = cvf_stream_kernel<4, 1, kS2Mixed, 1, 3>; break;  // light prefetch, <= 128 registers: 16 warps per SM with 128-thread CTAs
         case 11: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1, 3>; break;  // light prefetch, 168 registers
         case 12: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1, 0, 1>; break;  // packed exact adds
+        case 14: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1, 4, 0>; break;  // coefficient rows one step ahead
+        case 15: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1, 4, 1>; break;  // ... + packed exact adds
         case 13: kern = cvf_stream_kernel<4, 1, kS2Mixed, 1, 3, 1>; break;  // packed exact adds + light prefetch, 128 registers
         default: kern = cvf_stream_kernel<3, 1, kS2Mixed, 1>; break;
         }
@@ -292,6 +292,7 @@ int launch_cvf_stream(psm_ctx* c)
         case 10: kern = cvf_stream_kernel<4, 1, kS2Exact, 1, 3>; break;  // light prefetch, <= 128 registers
         case 11: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 3>; break;  // light prefetch, 168 registers
         case 12: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 1, 1>; break;  // packed exact adds
+        case 14: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 4, 0>; break;  // coefficient rows one step ahead
         default: kern = cvf_stream_kernel<3, 1, kS2Exact, 1, 1>; break;
         }
     }
@@ -424,7 +425,7 @@ int psm_destroy(psm_ctx* c)
     cudaFree(c->ab);
     cudaFree(c->guide_flags);
     cudaFree(c->pp_packed); cudaFree(c->pp_lut);
-    cudaFree(c->fgf_lo[0]); cudaFree(c->fgf_lo[1]); cudaFree(c->fgf_ab); cudaFree(c->fgf_mean); cudaFree(c->fgf_plan_i); cudaFree(c->fgf_plan_f);
+    cudaFree(c->fgf_lo[0]); cudaFree(c->fgf_lo[1]); cudaFree(c->fgf_mean); cudaFree(c->fgf_plan);
     for (int v = 0; v < 2; ++v) cudaFree(c->dis_pp[v]);
     for (int s = 0; s < kNumStages; ++s) {
         if (c->ev0[s]) cudaEventDestroy(c->ev0[s]);
@@ -615,51 +616,45 @@ int psm_cost_filter_fgf(psm_ctx* c, int s)
     g.ifx = 1.0 / ((double)g.w2 / g.W); g.ify = 1.0 / ((double)g.h2 / g.H);
     const size_t n2 = (size_t)g.w2 * g.h2;
     if (c->fgf_s != s) {   // (re)build buffers and the INTER_LINEAR plan for this rate
-        cudaFree(c->fgf_lo[0]); cudaFree(c->fgf_lo[1]); cudaFree(c->fgf_ab); cudaFree(c->fgf_mean); cudaFree(c->fgf_plan_i); cudaFree(c->fgf_plan_f);
-        c->fgf_lo[0] = c->fgf_lo[1] = c->fgf_ab = c->fgf_mean = nullptr; c->fgf_plan_i = nullptr; c->fgf_plan_f = nullptr; c->fgf_s = 0;
+        cudaFree(c->fgf_lo[0]); cudaFree(c->fgf_lo[1]); cudaFree(c->fgf_mean); cudaFree(c->fgf_plan);
+        c->fgf_lo[0] = c->fgf_lo[1] = c->fgf_mean = nullptr; c->fgf_plan = nullptr; c->fgf_s = 0;
         for (int v = 0; v < 2; ++v) PSM_CUDA(c, cudaMalloc(&c->fgf_lo[v], 12 * n2 * sizeof(float)));
-        PSM_CUDA(c, cudaMalloc(&c->fgf_ab, (size_t)4 * c->d_count * n2 * sizeof(float)));
         PSM_CUDA(c, cudaMalloc(&c->fgf_mean, (size_t)4 * c->d_count * n2 * sizeof(float)));
-        PSM_CUDA(c, cudaMalloc(&c->fgf_plan_i, (size_t)2 * (c->W + c->H) * sizeof(int)));
-        PSM_CUDA(c, cudaMalloc(&c->fgf_plan_f, (size_t)(c->W + c->H) * sizeof(float)));
+        PSM_CUDA(c, cudaMalloc(&c->fgf_plan, (size_t)(c->W + c->H) * sizeof(FgfTap)));
         // cv::resize INTER_LINEAR coordinates (OpenCV's own implementation; same expressions as the CPU restatement fgf_build in oracle/)
-        int* hi = new (std::nothrow) int[2 * (c->W + c->H)];
-        float* hf = new (std::nothrow) float[c->W + c->H];
-        if (!hi || !hf) { delete[] hi; delete[] hf; return fail(c, PSM_ENOMEM, "out of host memory"); }
-        int *x0 = hi, *x1 = hi + c->W, *y0 = hi + 2 * c->W, *y1 = y0 + c->H;
-        float *fx = hf, *fy = hf + c->W;
+        FgfTap* hp = new (std::nothrow) FgfTap[c->W + c->H];
+        if (!hp) return fail(c, PSM_ENOMEM, "out of host memory");
         { const double sc = (double)g.w2 / g.W;
           for (int x = 0; x < c->W; ++x) {
               float f = (float)((x + 0.5) * sc - 0.5); int i = (int)floorf(f); f -= (float)i;
               if (i < 0) { f = 0.f; i = 0; }
               if (i >= g.w2 - 1) { f = 0.f; i = g.w2 - 1; }
-              x0[x] = i; x1[x] = i + 1 < g.w2 ? i + 1 : g.w2 - 1; fx[x] = f; } }
+              hp[x].i0 = i; hp[x].i1 = i + 1 < g.w2 ? i + 1 : g.w2 - 1; hp[x].f = f; hp[x].pad = 0.f; } }
         { const double sc = (double)g.h2 / g.H;
           for (int y = 0; y < c->H; ++y) {
               float f = (float)((y + 0.5) * sc - 0.5); int i = (int)floorf(f); f -= (float)i;
-              y0[y] = i < 0 ? 0 : (i > g.h2 - 1 ? g.h2 - 1 : i);
-              y1[y] = i + 1 < 0 ? 0 : (i + 1 > g.h2 - 1 ? g.h2 - 1 : i + 1);
-              fy[y] = f; } }
-        cudaError_t e = cudaMemcpy(c->fgf_plan_i, hi, (size_t)2 * (c->W + c->H) * sizeof(int), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(c->fgf_plan_f, hf, (size_t)(c->W + c->H) * sizeof(float), cudaMemcpyHostToDevice);
-        delete[] hi; delete[] hf;
+              FgfTap& t = hp[c->W + y];
+              t.i0 = i < 0 ? 0 : (i > g.h2 - 1 ? g.h2 - 1 : i);
+              t.i1 = i + 1 < 0 ? 0 : (i + 1 > g.h2 - 1 ? g.h2 - 1 : i + 1);
+              t.f = f; t.pad = 0.f; } }
+        cudaError_t e = cudaMemcpy(c->fgf_plan, hp, (size_t)(c->W + c->H) * sizeof(FgfTap), cudaMemcpyHostToDevice);
+        delete[] hp;
         PSM_CUDA(c, e);
         c->fgf_s = s;
     }
     FgfPlan pl;
-    pl.x0 = c->fgf_plan_i; pl.x1 = c->fgf_plan_i + c->W; pl.y0 = c->fgf_plan_i + 2 * c->W; pl.y1 = pl.y0 + c->H;
-    pl.fx = c->fgf_plan_f; pl.fy = c->fgf_plan_f + c->W;
+    pl.x = static_cast<const FgfTap*>(c->fgf_plan);
+    pl.y = pl.x + c->W;
     if (int rc = stage_begin(c, 2)) return rc;
     if (int rc = stage_begin(c, 4)) return rc;
     for (int v = 0; v < 2; ++v) {
         dim3 blk(128), g2((g.w2 + 127) / 128, g.h2);
         fgf_guide_kernel<<<g2, blk, 0, c->stream>>>(c->guide[v], c->plane, g, kGifEps, c->fgf_lo[v]);
         PSM_LAUNCH_CHECK(c);
-        dim3 g3((g.w2 + 127) / 128, g.h2, c->d_count);
-        fgf_ab_kernel<<<g3, blk, 0, c->stream>>>(c->vol[v], c->plane, g, c->fgf_lo[v], c->fgf_ab);
-        PSM_LAUNCH_CHECK(c);
-        dim3 g4((g.w2 + 127) / 128, g.h2, c->d_count * 4);
-        fgf_mean_kernel<<<g4, blk, 0, c->stream>>>(c->fgf_ab, g, c->fgf_mean);
+        dim3 g3((g.w2 + kFgfTX - 1) / kFgfTX, (g.h2 + kFgfTY - 1) / kFgfTY, c->d_count);
+        const size_t fsmem = fgf_smem_bytes(g.K);
+        PSM_CUDA(c, cudaFuncSetAttribute(fgf_lowres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        fgf_lowres_kernel<<<g3, kFgfThreads, fsmem, c->stream>>>(c->vol[v], c->plane, g, c->fgf_lo[v], c->fgf_mean);
         PSM_LAUNCH_CHECK(c);
         dim3 g5((((c->W + 3) / 4) + 127) / 128, c->H, c->d_count);
         fgf_up_kernel<<<g5, blk, 0, c->stream>>>(c->vol[v], c->plane, c->guide[v], c->plane, g, pl, c->fgf_mean);

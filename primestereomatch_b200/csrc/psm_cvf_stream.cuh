@@ -142,7 +142,28 @@ __device__ __forceinline__ double widen_sg(float f)
 // anything (slow path): conversion pipe + exact rescale
 __device__ __forceinline__ double widen_any(float f) { return __dmul_rn((double)f, kScaleDown); }
 
-__device__ __forceinline__ float4 ldg4(const char* __restrict__ p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// PSM_KNOCKOUT (never defined in the product build): tools/cvf_knockout.cu compiles this header with single operation
+// classes removed -- results are wrong, only the TIME is of interest -- to measure what the kernel is sensitive to.
+// bit 0 shuffles, bit 1 tensor-memory ring, bit 2 guide loads, bit 3 stores, bit 4 stage-1 widening + fp64 running sums,
+// bit 5 volume (p) loads.
+#ifndef PSM_KNOCKOUT
+#define PSM_KNOCKOUT 0
+#endif
+__device__ __forceinline__ float4 ko_fake(const char* p)
+{
+    const float f = __int_as_float(0x3f000000 | ((int)(size_t)p & 0xffff));
+    return make_float4(f, f, f, f);
+}
+__device__ __forceinline__ float4 ldg4(const char* __restrict__ p)    // volume rows
+{
+    if (PSM_KNOCKOUT & 32) return ko_fake(p);
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ float4 ldg4g(const char* __restrict__ p)   // guide rows
+{
+    if (PSM_KNOCKOUT & 4) return ko_fake(p);
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
 
 __device__ __forceinline__ void prefetch_l1(const char* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
@@ -157,10 +178,14 @@ __device__ __forceinline__ f2x2 hsum8f(const f2x2& c)
     const float c0 = c.lo.x, c1 = c.lo.y, c2 = c.hi.x, c3 = c.hi.y;
     const float P2 = __fadd_rn(c0, c1), P3 = __fadd_rn(P2, c2), Tt = __fadd_rn(P3, c3);
     const float S2 = __fadd_rn(c2, c3), S3 = __fadd_rn(c1, S2);
+#if PSM_KNOCKOUT & 1
+    const float Tn = Tt, Q1 = c0, Q2 = P2, Q3 = P3;
+#else
     const float Tn = __shfl_down_sync(0xffffffffu, Tt, 1);
     const float Q1 = __shfl_down_sync(0xffffffffu, c0, 2);
     const float Q2 = __shfl_down_sync(0xffffffffu, P2, 2);
     const float Q3 = __shfl_down_sync(0xffffffffu, P3, 2);
+#endif
     f2x2 h;
     h.lo.x = __fadd_rn(Tt, Tn);
     h.lo.y = __fadd_rn(__fadd_rn(S3, Tn), Q1);
@@ -182,6 +207,11 @@ __device__ __forceinline__ f2x2 hsum8f(const f2x2& c)
 __device__ __forceinline__ void tmem_ld16(unsigned taddr, f2x2 (&v)[4])
 {
     unsigned r[16];
+    if (PSM_KNOCKOUT & 2) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = {make_float2(1.f, 2.f), make_float2(3.f, (float)taddr)};
+        return;
+    }
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
@@ -199,6 +229,7 @@ __device__ __forceinline__ void tmem_st16(unsigned taddr, const f2x2 (&v)[4])
         r[4 * q] = __float_as_uint(v[q].lo.x); r[4 * q + 1] = __float_as_uint(v[q].lo.y);
         r[4 * q + 2] = __float_as_uint(v[q].hi.x); r[4 * q + 3] = __float_as_uint(v[q].hi.y);
     }
+    if (PSM_KNOCKOUT & 2) return;
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
                  :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                     "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
@@ -254,7 +285,8 @@ __device__ __forceinline__ float4 lds4(unsigned addr)
 // PA  : 1 = adds / subtracts of products as packed FFMA2 with a run-time unit multiplier (exact, see fma2)
 // PF  : 1 = prefetch the next step's guide rows into L1;  2 = stage the guide rows in shared memory with bulk async
 //       copies (TMA) issued two steps ahead by one lane per CTA (needs TM = 1: the ring is not in shared memory);
-//       3 = light prefetch (only the newest p row a step ahead; everything else is an L1 hit with the ring in TMEM)
+//       3 = light prefetch (only the newest p row a step ahead; everything else is an L1 hit with the ring in TMEM);
+//       4 = the ten coefficient rows are loaded one step ahead as well (40 more live registers)
 // register budgets by MINB: 3 -> 168 regs (3 CTAs x 128 thr or 4 x 96: 12 warps/SM); 4 -> 128 regs (16 warps);
 // 5 -> 144 regs (2 CTAs x 224 thr = 14 warps, two TMEM column blocks per lane quarter); 6 -> 152 regs (13 warps)
 constexpr int cvf_max_regs(int minb) { return minb == 3 ? 168 : (minb == 4 ? 128 : (minb == 5 ? 144 : 152)); }
@@ -402,9 +434,9 @@ cvf_stream_kernel(const CvfParams P)
     auto load_at = [&](size_t ro) {  // ro: byte offset of the row
         RowIn x;
         x.p = ldg4(vin + ro);
-        x.i0 = ldg4(Gi + ro);
-        x.i1 = ldg4(Gi + (planeB + ro));
-        x.i2 = ldg4(Gi + (2 * planeB + ro));
+        x.i0 = ldg4g(Gi + ro);
+        x.i1 = ldg4g(Gi + (planeB + ro));
+        x.i2 = ldg4g(Gi + (2 * planeB + ro));
         return x;
     };
     auto load_row = [&](int r) { return load_at((size_t)reflect101(r, H) * rowB); };
@@ -416,6 +448,7 @@ cvf_stream_kernel(const CvfParams P)
     auto acc_row = [&](const RowIn& x, auto wid_tag, auto sub_tag) {
         constexpr int WID = decltype(wid_tag)::value;
         constexpr bool SUB = decltype(sub_tag)::value;
+        if (PSM_KNOCKOUT & 16) { S1[0][0] = __hiloint2double(__float_as_int(x.p.x), __float_as_int(x.i0.y)); return; }
         const f2x2 p = from4(x.p);
         const f2x2 m0 = mul2(from4(x.i0), p), m1 = mul2(from4(x.i1), p), m2 = mul2(from4(x.i2), p);  // CVF.cpp:87
         auto w = [](float f) { return WID == 0 ? (double)f : (WID == 1 ? widen_nn(f) : widen_any(f)); };
@@ -451,7 +484,7 @@ cvf_stream_kernel(const CvfParams P)
     };
     auto load_guide = [&](size_t ro, float4 (&g4)[10]) {
 #pragma unroll
-        for (int q = 0; q < 10; ++q) g4[q] = ldg4(Ga + ((size_t)(kGuideMean + q) * planeB + ro));
+        for (int q = 0; q < 10; ++q) g4[q] = ldg4g(Ga + ((size_t)(kGuideMean + q) * planeB + ro));
     };
     auto mean4 = [](const double (&h)[4], double scale) {
         f2x2 m;
@@ -511,7 +544,7 @@ cvf_stream_kernel(const CvfParams P)
         f2x2 qv = xadd(mb[3], mul2(mb[0], from4(i0)));
         qv = xadd(qv, mul2(mb[1], from4(i1)));
         qv = xadd(qv, mul2(mb[2], from4(i2)));
-        if (store_ok) *reinterpret_cast<float4*>(vout + ro) = to4(qv);
+        if (store_ok && !((PSM_KNOCKOUT & 8) && qv.lo.x != 12345.f)) *reinterpret_cast<float4*>(vout + ro) = to4(qv);
     };
     // EXACT: stage-2 row sums of S2 -> q for one output row
     auto emit = [&](size_t ro, const float4& i0, const float4& i1, const float4& i2) {
@@ -600,7 +633,7 @@ cvf_stream_kernel(const CvfParams P)
             const int y = (top && t == 4) ? e : t - 3;
             if (y < Y0 || y >= Y1) continue;
             const size_t ro = (size_t)y * rowB;
-            const float4 o0 = ldg4(Go + ro), o1 = ldg4(Go + (planeB + ro)), o2 = ldg4(Go + (2 * planeB + ro));
+            const float4 o0 = ldg4g(Go + ro), o1 = ldg4g(Go + (planeB + ro)), o2 = ldg4g(Go + (2 * planeB + ro));
             if (!MIXED) {
                 emit(ro, o0, o1, o2);
             } else {
@@ -643,13 +676,21 @@ cvf_stream_kernel(const CvfParams P)
         // One steady step.  SLOW (compile time) selects the F2F widening for rows outside the integer
         // domain; the fast loop below leaves for the slow loop the first time a vote says so and never
         // comes back (sticky), so the fast loop is straight-line code.
+        float4 g4n[PF == 4 ? 10 : 1];   // PF == 4: the coefficient rows of the NEXT step, loaded right after this step's were consumed
+        if (PF == 4) {
+#pragma unroll
+            for (int q = 0; q < (PF == 4 ? 10 : 1); ++q) g4n[q] = ldg4(Ga + ((size_t)(kGuideMean + q) * planeB + ro_t));
+        }
         auto steady = [&](auto slow_tag) {
             constexpr bool SLOW = decltype(slow_tag)::value;
-            const float4 o0 = ldg4(Go + ro_y), o1 = ldg4(Go + (planeB + ro_y)), o2 = ldg4(Go + (2 * planeB + ro_y));
+            const float4 o0 = ldg4g(Go + ro_y), o1 = ldg4g(Go + (planeB + ro_y)), o2 = ldg4g(Go + (2 * planeB + ro_y));
             f2x2 av[4];
             {   // stage 1 of a,b row ro_t: S1 += newest, row sums -> a,b, S1 -= oldest; refills xn / xo
                 float4 g4[10];
-                load_guide(ro_t, g4);
+                if (PF == 4) {
+#pragma unroll
+                    for (int q = 0; q < 10; ++q) g4[q] = g4n[PF == 4 ? q : 0];
+                } else load_guide(ro_t, g4);
                 if (PF) {   // next step's coefficient rows and output-column guide rows -> L1 (one step = thousands of cycles ahead)
 #pragma unroll
                     for (int q = 0; q < 10; ++q) prefetch_l1(Ga + ((size_t)(kGuideMean + q) * planeB + ro_t + rowB));
@@ -660,6 +701,10 @@ cvf_stream_kernel(const CvfParams P)
                 ro_n += rowB;
                 xn = load_at(ro_n);     // into the registers add_row just released
                 coeffs(g4, av);
+                if (PF == 4) {   // next step's coefficient rows: a whole stage 2 (and the tail of stage 1) ahead of their first use
+#pragma unroll
+                    for (int q = 0; q < (PF == 4 ? 10 : 1); ++q) g4n[q] = ldg4(Ga + ((size_t)(kGuideMean + q) * planeB + ro_t + rowB));
+                }
                 sub_row(xo, SLOW);
                 ro_o += rowB;
                 xo = load_at(ro_o);
@@ -724,7 +769,7 @@ cvf_stream_kernel(const CvfParams P)
                     ro_o += rowB;
                     ro_t += rowB;
                 }
-                const float4 o0 = ldg4(Go + ro_y), o1 = ldg4(Go + (planeB + ro_y)), o2 = ldg4(Go + (2 * planeB + ro_y));
+                const float4 o0 = ldg4g(Go + ro_y), o1 = ldg4g(Go + (planeB + ro_y)), o2 = ldg4g(Go + (2 * planeB + ro_y));
                 if (!MIXED) {
                     f2x2 old[4];
                     ring_wait_st();

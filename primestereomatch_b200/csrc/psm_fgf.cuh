@@ -14,8 +14,8 @@
 //
 // Work split (nothing like the reference's per-slice Mat pipeline of ~40 OpenCV calls):
 //   fgf_guide_kernel : per view, per low-res pixel: channel means, (Sigma + eps I)^-1          (once per frame)
-//   fgf_ab_kernel    : per slice, per low-res pixel: p and I*p box means -> a (3), b            (reads 1/s^2 of p)
-//   fgf_mean_kernel  : per slice: K x K box means of a, b at low resolution
+//   fgf_lowres_kernel: per slice tile, both low-res stages in shared memory (separable fp64 box sums): p and I*p box
+//                      means -> a (3), b -> their box means                                      (reads 1/s^2 of p)
 //   fgf_up_kernel    : per full-res pixel group (4 px, 128-bit store): bilinear up-sampling of the four means and
 //                      q = ((ma_r*I_r + ma_g*I_g) + ma_b*I_b) + mb, written over p (p is only read at the sample
 //                      points by the earlier kernels, so the filter runs in place)
@@ -83,59 +83,141 @@ __global__ void fgf_guide_kernel(const float* __restrict__ I /* 3 full-res plane
     lo[9 * n2 + o] = __fdiv_rn(igg, det); lo[10 * n2 + o] = __fdiv_rn(igb, det); lo[11 * n2 + o] = __fdiv_rn(ibb, det);
 }
 
-// a (3), b of every owned slice at low resolution: ab[(slice * 4 + k) * n2 + pixel]
-__global__ void fgf_ab_kernel(const float* __restrict__ vol, size_t vplane, FgfGeom g, const float* __restrict__ lo, float* __restrict__ ab)
+// Both low-resolution stages of one slice tile in ONE kernel (shared-memory tiles, separable fp64 box sums):
+//   region R1 = tile + 2h halo (h = K/2): p and I*p at the NN sample points, widened once into shared memory (doubles)
+//   horizontal K-sums -> vertical K-sums -> box means on R2 = tile + h halo -> a (3), b there (floats, shared memory)
+//   horizontal / vertical K-sums of a, b -> their box means on the tile -> global memory (4 planes per slice)
+// Cells outside the low-res image hold the value of the BORDER_REFLECT_101 pixel; because reflect-101 is an even
+// symmetry and the fp64 sums are exact, the box around a halo cell equals the box around the pixel it mirrors, so the
+// second stage sees exactly cv::blur's border handling of the first stage's output.
+constexpr int kFgfTX = 32, kFgfTY = 16, kFgfThreads = 256;
+
+__host__ __device__ inline size_t fgf_smem_bytes(int K)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, dl = blockIdx.z;
-    if (x >= g.w2 || y >= g.h2) return;
-    const int a = g.K / 2;
-    const size_t n2 = (size_t)g.w2 * g.h2, o = (size_t)y * g.w2 + x;
+    const int h = K / 2;
+    // row strides are made odd: the sliding sums run one thread per row, so consecutive lanes are one row stride apart
+    const size_t r1 = (size_t)((kFgfTX + 4 * h) | 1) * (kFgfTY + 4 * h);    // inputs (4 planes of doubles)
+    const size_t hs = (size_t)((kFgfTX + 2 * h) | 1) * (kFgfTY + 4 * h);    // horizontal sums (4 planes of doubles)
+    const size_t r2 = (size_t)((kFgfTX + 2 * h) | 1) * (kFgfTY + 2 * h);    // a, b (4 planes of floats)
+    return (r1 + hs) * 4 * sizeof(double) + r2 * 4 * sizeof(float);
+}
+
+__global__ void __launch_bounds__(kFgfThreads) fgf_lowres_kernel(const float* __restrict__ vol, size_t vplane, FgfGeom g,
+                                                                 const float* __restrict__ lo, float* __restrict__ mean)
+{
+    extern __shared__ double fsm[];
+    const int h = g.K / 2, K = g.K;
+    const int W1n = kFgfTX + 4 * h, H1 = kFgfTY + 4 * h;     // input region (W1n columns used, odd stride W1)
+    const int W2n = kFgfTX + 2 * h, H2 = kFgfTY + 2 * h;     // a,b region
+    const int W1 = W1n | 1, W2 = W2n | 1;
+    constexpr int kTXs = kFgfTX | 1;                          // stage-2 row stride
+    double* in = fsm;                                        // [4][H1][W1]
+    double* hs = in + (size_t)4 * W1 * H1;                   // [4][H1][W2]  (stage 2 reuses it as [4][H2][kTXs])
+    float* ab = reinterpret_cast<float*>(hs + (size_t)4 * W2 * H1);   // [4][H2][W2]
+    const int x0 = blockIdx.x * kFgfTX, y0 = blockIdx.y * kFgfTY, dl = blockIdx.z;
+    const size_t n2 = (size_t)g.w2 * g.h2;
     const float* p = vol + (size_t)dl * vplane;
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    for (int dy = -a; dy <= a; ++dy) {
-        const int ly = reflect101(y + dy, g.h2);
-        const int yy = fgf_nn(ly, g.ify, g.H);
-        for (int dx = -a; dx <= a; ++dx) {
-            const int lx = reflect101(x + dx, g.w2);
-            const float pv = __ldg(p + (size_t)yy * g.Wp + fgf_nn(lx, g.ifx, g.W));   // resize(p, INTER_NN), :69
+    const double scale = 1.0 / ((double)K * K);
+    const int tx0 = threadIdx.x & 31, ty0 = threadIdx.x >> 5;   // 32 x 8 thread grid: rows by warps, columns by lanes (no runtime division)
+    constexpr int kRowsPerPass = kFgfThreads / 32;
+    // ---- inputs: p2 = resize(p, INTER_NN) (:69) and I*p2 (:175-177) on R1, widened once
+    for (int ry = ty0; ry < H1; ry += kRowsPerPass) {
+        const int ly = reflect101(y0 - 2 * h + ry, g.h2);
+        const float* prow = p + (size_t)fgf_nn(ly, g.ify, g.H) * g.Wp;
+        for (int rx = tx0; rx < W1n; rx += 32) {
+            const int lx = reflect101(x0 - 2 * h + rx, g.w2);
+            const float pv = __ldg(prow + fgf_nn(lx, g.ifx, g.W));
             const size_t q = (size_t)ly * g.w2 + lx;
-            s0 += (double)pv;
-            s1 += (double)fmul(__ldg(lo + q), pv);
-            s2 += (double)fmul(__ldg(lo + n2 + q), pv);
-            s3 += (double)fmul(__ldg(lo + 2 * n2 + q), pv);
+            const int i = ry * W1 + rx;
+            in[i] = (double)pv;
+            in[(size_t)W1 * H1 + i] = (double)fmul(__ldg(lo + q), pv);
+            in[(size_t)2 * W1 * H1 + i] = (double)fmul(__ldg(lo + n2 + q), pv);
+            in[(size_t)3 * W1 * H1 + i] = (double)fmul(__ldg(lo + 2 * n2 + q), pv);
         }
     }
-    const double scale = 1.0 / ((double)g.K * g.K);
-    const float mp = (float)(s0 * scale), mIp0 = (float)(s1 * scale), mIp1 = (float)(s2 * scale), mIp2 = (float)(s3 * scale);
-    const float m0 = lo[3 * n2 + o], m1 = lo[4 * n2 + o], m2 = lo[5 * n2 + o];
-    const float c0 = fsub(mIp0, fmul(m0, mp)), c1 = fsub(mIp1, fmul(m1, mp)), c2 = fsub(mIp2, fmul(m2, mp));   // :178-180
-    const float irr = lo[6 * n2 + o], irg = lo[7 * n2 + o], irb = lo[8 * n2 + o], igg = lo[9 * n2 + o], igb = lo[10 * n2 + o], ibb = lo[11 * n2 + o];
-    const float ar = fadd(fadd(fmul(irr, c0), fmul(irg, c1)), fmul(irb, c2));   // :182-184
-    const float ag = fadd(fadd(fmul(irg, c0), fmul(igg, c1)), fmul(igb, c2));
-    const float ab_ = fadd(fadd(fmul(irb, c0), fmul(igb, c1)), fmul(ibb, c2));
-    const float b = fsub(fsub(fsub(mp, fmul(ar, m0)), fmul(ag, m1)), fmul(ab_, m2));   // :186
-    float* out = ab + (size_t)dl * 4 * n2 + o;
-    out[0] = ar; out[n2] = ag; out[2 * n2] = ab_; out[3 * n2] = b;
-}
-
-// K x K box means of the four coefficient planes of every slice
-__global__ void fgf_mean_kernel(const float* __restrict__ ab, FgfGeom g, float* __restrict__ mean)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= g.w2 || y >= g.h2) return;
-    const int a = g.K / 2;
-    const size_t n2 = (size_t)g.w2 * g.h2;
-    const float* src = ab + (size_t)blockIdx.z * n2;   // blockIdx.z = slice * 4 + plane
-    double s = 0;
-    for (int dy = -a; dy <= a; ++dy) {
-        const float* row = src + (size_t)reflect101(y + dy, g.h2) * g.w2;
-        for (int dx = -a; dx <= a; ++dx) s += (double)__ldg(row + reflect101(x + dx, g.w2));
+    __syncthreads();
+    // Box sums as SLIDING fp64 sums (+ entering, - leaving): two shared-memory reads per output instead of K.  The sums
+    // are exact (<= 81 floats of bounded range), so the sliding form gives the same bits as the direct form.
+    // ---- stage 1, horizontal: one thread per (plane, row) slides along the W2 outputs
+    for (int task = threadIdx.x; task < 4 * H1; task += kFgfThreads) {
+        const double* src = in + (size_t)task * W1;      // task = plane * H1 + row
+        double* dst = hs + (size_t)task * W2;
+        double sacc = 0;
+        for (int d = 0; d < K; ++d) sacc += src[d];
+        dst[0] = sacc;
+        for (int x = 1; x < W2n; ++x) { sacc = (sacc + src[x + K - 1]) - src[x - 1]; dst[x] = sacc; }
     }
-    mean[(size_t)blockIdx.z * n2 + (size_t)y * g.w2 + x] = (float)(s * (1.0 / ((double)g.K * g.K)));
+    __syncthreads();
+    // ---- stage 1, vertical: one thread per (plane, column) slides down the H2 outputs -> box means (floats) into `ab`
+    for (int task = threadIdx.x; task < 4 * W2n; task += kFgfThreads) {
+        const int k = task / W2n, rx = task - k * W2n;
+        const double* src = hs + (size_t)k * H1 * W2 + rx;
+        float* dst = ab + (size_t)k * W2 * H2 + rx;
+        double sacc = 0;
+        for (int d = 0; d < K; ++d) sacc += src[(size_t)d * W2];
+        dst[0] = (float)(sacc * scale);
+        for (int y = 1; y < H2; ++y) {
+            sacc = (sacc + src[(size_t)(y + K - 1) * W2]) - src[(size_t)(y - 1) * W2];
+            dst[(size_t)y * W2] = (float)(sacc * scale);
+        }
+    }
+    __syncthreads();
+    // ---- a, b on R2 from the four means of every cell, in place (fastguidedfilter.cpp:178-186)
+    for (int ry = ty0; ry < H2; ry += kRowsPerPass) {
+        const int ly = reflect101(y0 - h + ry, g.h2);
+        for (int rx = tx0; rx < W2n; rx += 32) {
+            const int i = ry * W2 + rx;
+            const float mp = ab[i], mIp0 = ab[(size_t)W2 * H2 + i], mIp1 = ab[(size_t)2 * W2 * H2 + i], mIp2 = ab[(size_t)3 * W2 * H2 + i];
+            const int lx = reflect101(x0 - h + rx, g.w2);
+            const size_t o = (size_t)ly * g.w2 + lx;
+            const float m0 = __ldg(lo + 3 * n2 + o), m1 = __ldg(lo + 4 * n2 + o), m2 = __ldg(lo + 5 * n2 + o);
+            const float c0 = fsub(mIp0, fmul(m0, mp)), c1 = fsub(mIp1, fmul(m1, mp)), c2 = fsub(mIp2, fmul(m2, mp));
+            const float irr = __ldg(lo + 6 * n2 + o), irg = __ldg(lo + 7 * n2 + o), irb = __ldg(lo + 8 * n2 + o);
+            const float igg = __ldg(lo + 9 * n2 + o), igb = __ldg(lo + 10 * n2 + o), ibb = __ldg(lo + 11 * n2 + o);
+            const float ar = fadd(fadd(fmul(irr, c0), fmul(irg, c1)), fmul(irb, c2));
+            const float ag = fadd(fadd(fmul(irg, c0), fmul(igg, c1)), fmul(igb, c2));
+            const float ab_ = fadd(fadd(fmul(irb, c0), fmul(igb, c1)), fmul(ibb, c2));
+            const float bb = fsub(fsub(fsub(mp, fmul(ar, m0)), fmul(ag, m1)), fmul(ab_, m2));
+            ab[i] = ar; ab[(size_t)W2 * H2 + i] = ag; ab[(size_t)2 * W2 * H2 + i] = ab_; ab[(size_t)3 * W2 * H2 + i] = bb;
+        }
+    }
+    __syncthreads();
+    // ---- stage 2, horizontal: (plane, row) tasks slide along the TX outputs of the tile
+    for (int task = threadIdx.x; task < 4 * H2; task += kFgfThreads) {
+        const float* src = ab + (size_t)task * W2;
+        double* dst = hs + (size_t)task * kTXs;
+        double sacc = 0;
+        for (int d = 0; d < K; ++d) sacc += (double)src[d];
+        dst[0] = sacc;
+        for (int x = 1; x < kFgfTX; ++x) { sacc = (sacc + (double)src[x + K - 1]) - (double)src[x - 1]; dst[x] = sacc; }
+    }
+    __syncthreads();
+    // ---- stage 2, vertical: (plane, column) tasks slide down the TY outputs -> means staged in `in` as floats [TY][TX][4]
+    float* stage = reinterpret_cast<float*>(in);
+    for (int task = threadIdx.x; task < 4 * kFgfTX; task += kFgfThreads) {
+        const int k = task / kFgfTX, tx = task - k * kFgfTX;
+        const double* src = hs + (size_t)k * H2 * kTXs + tx;
+        double sacc = 0;
+        for (int d = 0; d < K; ++d) sacc += src[(size_t)d * kTXs];
+        stage[(0 * kFgfTX + tx) * 4 + k] = (float)(sacc * scale);
+        for (int y = 1; y < kFgfTY; ++y) {
+            sacc = (sacc + src[(size_t)(y + K - 1) * kTXs]) - src[(size_t)(y - 1) * kTXs];
+            stage[(y * kFgfTX + tx) * 4 + k] = (float)(sacc * scale);
+        }
+    }
+    __syncthreads();
+    // ---- (mean_a_r, mean_a_g, mean_a_b, mean_b) of the tile, interleaved per pixel, coalesced 128-bit stores (:188-191)
+    for (int ty = ty0; ty < kFgfTY; ty += kRowsPerPass) {
+        const int x = x0 + tx0, y = y0 + ty;
+        if (x >= g.w2 || y >= g.h2) continue;
+        reinterpret_cast<float4*>(mean)[(size_t)dl * n2 + (size_t)y * g.w2 + x] = reinterpret_cast<const float4*>(stage)[ty * kFgfTX + tx0];
+    }
 }
 
-// up-sampling plan of one axis: i0, i1 (low-res indices) and the float weight f of i1 (OpenCV's own formula, built on the host)
-struct FgfPlan { const int* x0; const int* x1; const float* fx; const int* y0; const int* y1; const float* fy; };
+// up-sampling plan (OpenCV's own INTER_LINEAR formula, built on the host): per destination column / row the two source
+// indices and the float weight of the second one, 16 bytes each so that one 128-bit load fetches an entry
+struct alignas(16) FgfTap { int i0, i1; float f, pad; };
+struct FgfPlan { const FgfTap* x; const FgfTap* y; };
 
 __global__ void __launch_bounds__(128) fgf_up_kernel(float* __restrict__ vol, size_t vplane, const float* __restrict__ I, size_t plane,
                                                      FgfGeom g, FgfPlan pl, const float* __restrict__ mean)
@@ -143,28 +225,34 @@ __global__ void __launch_bounds__(128) fgf_up_kernel(float* __restrict__ vol, si
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, dl = blockIdx.z;
     if (x4 >= g.W) return;
     const size_t n2 = (size_t)g.w2 * g.h2;
-    const float* m = mean + (size_t)dl * 4 * n2;
-    const int r0 = pl.y0[y], r1 = pl.y1[y];
-    const float fy = pl.fy[y], b0 = fsub(1.f, fy);
+    const float4* m = reinterpret_cast<const float4*>(mean) + (size_t)dl * n2;   // (ma_r, ma_g, ma_b, mb) per low-res pixel
+    const FgfTap ty = pl.y[y];
+    const float fy = ty.f, b0 = fsub(1.f, fy);
+    const float4* row0 = m + (size_t)ty.i0 * g.w2;
+    const float4* row1 = m + (size_t)ty.i1 * g.w2;
+    const size_t o4 = (size_t)y * g.Wp + x4;
+    float i0[4], i1[4], i2[4];
+    if (x4 + 3 < g.Wp) {   // rows are padded to a multiple of 4 floats: a full 128-bit read is always inside the row
+        const float4 a = __ldg(reinterpret_cast<const float4*>(I + o4)), b = __ldg(reinterpret_cast<const float4*>(I + plane + o4)),
+                     c = __ldg(reinterpret_cast<const float4*>(I + 2 * plane + o4));
+        i0[0] = a.x; i0[1] = a.y; i0[2] = a.z; i0[3] = a.w; i1[0] = b.x; i1[1] = b.y; i1[2] = b.z; i1[3] = b.w;
+        i2[0] = c.x; i2[1] = c.y; i2[2] = c.z; i2[3] = c.w;
+    }
     float q[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int x = x4 + j;
         if (x >= g.W) { q[j] = 0.f; continue; }
-        const int c0 = pl.x0[x], c1 = pl.x1[x];
-        const float fx = pl.fx[x], a0 = fsub(1.f, fx);
-        float up[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float* mk = m + (size_t)k * n2;
-            const float h0 = fadd(fmul(__ldg(mk + (size_t)r0 * g.w2 + c0), a0), fmul(__ldg(mk + (size_t)r0 * g.w2 + c1), fx));
-            const float h1 = fadd(fmul(__ldg(mk + (size_t)r1 * g.w2 + c0), a0), fmul(__ldg(mk + (size_t)r1 * g.w2 + c1), fx));
-            up[k] = fadd(fmul(h0, b0), fmul(h1, fy));   // rows after columns, like cv::resize
-        }
-        const size_t o = (size_t)y * g.Wp + x;
-        q[j] = fadd(fadd(fadd(fmul(up[0], I[o]), fmul(up[1], I[plane + o])), fmul(up[2], I[2 * plane + o])), up[3]);   // :196
+        const FgfTap tx = pl.x[x];
+        const float fx = tx.f, a0 = fsub(1.f, fx);
+        const float4 s00 = __ldg(row0 + tx.i0), s01 = __ldg(row0 + tx.i1), s10 = __ldg(row1 + tx.i0), s11 = __ldg(row1 + tx.i1);
+        // rows after columns, like cv::resize: h = S0*(1-fx) + S1*fx per source row, then h0*(1-fy) + h1*fy
+#define PSM_FGF_UP(c) fadd(fmul(fadd(fmul(s00.c, a0), fmul(s01.c, fx)), b0), fmul(fadd(fmul(s10.c, a0), fmul(s11.c, fx)), fy))
+        const float ur = PSM_FGF_UP(x), ug = PSM_FGF_UP(y), ub = PSM_FGF_UP(z), ubb = PSM_FGF_UP(w);
+#undef PSM_FGF_UP
+        q[j] = fadd(fadd(fadd(fmul(ur, i0[j]), fmul(ug, i1[j])), fmul(ub, i2[j])), ubb);   // :196
     }
-    float* dst = vol + (size_t)dl * vplane + (size_t)y * g.Wp + x4;
+    float* dst = vol + (size_t)dl * vplane + o4;
     if (x4 + 3 < g.W) __stcs(reinterpret_cast<float4*>(dst), make_float4(q[0], q[1], q[2], q[3]));
     else for (int j = 0; j < 4 && x4 + j < g.W; ++j) dst[j] = q[j];
 }

@@ -277,10 +277,14 @@ __device__ __forceinline__ void hsum8(const double c[4], double h[4])
 {
     const double P1 = c[0], P2 = c[0] + c[1], P3 = P2 + c[2], Tt = P3 + c[3];
     const double S1 = c[3], S2 = c[2] + c[3], S3 = c[1] + S2;
+#if defined(PSM_KNOCKOUT) && (PSM_KNOCKOUT & 1)   // diagnostics only, see psm_cvf_stream.cuh
+    const double Tn = Tt, Q1 = P1, Q2 = P2, Q3 = P3;
+#else
     const double Tn = __shfl_down_sync(0xffffffffu, Tt, 1);
     const double Q1 = __shfl_down_sync(0xffffffffu, P1, 2);
     const double Q2 = __shfl_down_sync(0xffffffffu, P2, 2);
     const double Q3 = __shfl_down_sync(0xffffffffu, P3, 2);
+#endif
     h[0] = Tt + Tn;
     h[1] = (S3 + Tn) + Q1;
     h[2] = (S2 + Tn) + Q2;

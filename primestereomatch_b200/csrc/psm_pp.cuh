@@ -17,7 +17,7 @@
 // B200 mapping (nothing like the reference's serial column scan with necklace tables): one WARP per pixel,
 //   the 361 window taps dealt round-robin to the 32 lanes (12 rounds), each tap one 4-byte load of a packed
 //   u32 image (disparity << 24 | R6 << 16 | G6 << 8 | B6);
-//   per round the lanes holding the same disparity combine their weights (ballot + __reduce_add_sync) and one
+//   per round the lanes holding the same disparity combine their weights (__match_any_sync + __reduce_add_sync) and one
 //   lane adds the sum to a 256-bin histogram in shared memory (1 KB per warp): integer sums, order-independent;
 //   then each lane scans 8 bins, a warp prefix sum finds the first bin where 2*cum >= total.
 #pragma once
@@ -78,18 +78,11 @@ __global__ void __launch_bounds__(kPpWarps * 32) pp_wmf_kernel(const uint32_t* _
                 dq = cq >> 24;
             }
             total += w;
-            // combine the taps that carry the same disparity (neighbouring pixels usually do) before touching shared memory
-            unsigned todo = __ballot_sync(0xffffffffu, ok);
-            while (todo) {
-                const int leader = __ffs(todo) - 1;
-                const unsigned v = __shfl_sync(0xffffffffu, dq, leader);
-                const unsigned same = __ballot_sync(0xffffffffu, ok && dq == v);
-                if (ok && dq == v) {
-                    const uint32_t s = __reduce_add_sync(same, w);
-                    if (lane == leader) h[v] += s;
-                }
-                todo &= ~same;
-            }
+            // combine the taps that carry the same disparity (neighbouring pixels usually do) before touching shared memory:
+            // every lane learns its peer set in one MATCH, the peers add their weights with one REDUX, the lowest peer owns the bin
+            const unsigned peers = __match_any_sync(0xffffffffu, dq);
+            const uint32_t s = __reduce_add_sync(peers, w);
+            if (ok && lane == __ffs(peers) - 1) h[dq] += s;
         }
         __syncwarp();
         total = __reduce_add_sync(0xffffffffu, total);

@@ -81,7 +81,7 @@ def test_mixed_mode_matches_its_model_and_tolerance(scene, scenes, oracle, oracl
         assert int((diff > 0).sum()) == 0          # in fact identical maps on both scenes
 
 
-@pytest.mark.parametrize("variant", [0, 9, 10, 12, 13])
+@pytest.mark.parametrize("variant", [0, 9, 10, 12, 13, 14, 15])
 @pytest.mark.parametrize("W,H,D", [(16, 16, 4), (17, 23, 5), (113, 40, 8), (130, 50, 9), (225, 33, 16),
                                    (451, 64, 12), (64, 300, 6), (340, 17, 3)])
 def test_mixed_mode_ragged_sizes(W, H, D, variant, oracle):
