@@ -61,6 +61,7 @@ struct psm_ctx {
     int p2p_nimported = 0, p2p_nranks = 0, p2p_rank = 0;
     unsigned* p2p_counter = nullptr;        // device-local CTA counter of the publishing kernels
     unsigned p2p_seq = 0;                   // frame sequence number of the device-side exchange flags
+    unsigned p2p_waited_seq = 0;            // last sequence number whose DONE flags a wait kernel was enqueued for
     int p2p_sync = 1;                       // 1: device-side ARRIVE/DONE flags; 0: the caller separates the kernels by its own barriers
     float* alloc[16] = {};                  // raw cudaMalloc pointers behind the halo-offset pointers above
     int nalloc = 0;
@@ -237,11 +238,28 @@ int launch_cvf_stream(psm_ctx* c)
     const int nthreads = c->cvf_threads > 0 ? c->cvf_threads : auto_threads;
     const int wpc = nthreads / 32;
     P.ndgroups = (c->d_count + wpc - 1) / wpc;
-    // enough CTAs for several waves over 148 SMs x 3 resident CTAs, but segments no shorter than
-    // ~128 rows (each segment pays ~11 warm-up rows)
-    int target_rows = 256;
-    const long ctas_1seg = 2L * P.nstrips * P.ndgroups;
-    if (ctas_1seg * (c->H / 256 > 0 ? c->H / 256 : 1) < 148 * 3 * 4) target_rows = 128;
+    // Row segmentation, wave-aware: every segment pays ~11 warm-up rows, and the grid runs in waves of (SMs x resident
+    // CTAs) -- with few slices per rank (16 at 8 GPUs) a badly chosen segment count leaves the last wave nearly empty
+    // (4 segments: 576 CTAs over 444 slots = 2 waves; 3 segments: 432 CTAs = 1 wave).  Pick the count that minimises
+    // waves x (rows per segment + warm-up).
+    int best_ns = 1, best_rows = (c->H + 7) & ~7;
+    {
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+        const long slots = (long)nsm * (65536 / (168 * nthreads));        // resident CTAs: 168 registers per thread
+        long best_cost = -1;
+        for (int want = 1; want <= 12; ++want) {
+            int ns = 1, rows = c->H;
+            plan_segments(c->H, (c->H + want - 1) / want, &ns, &rows);
+            const long ctas = 2L * ns * P.nstrips * P.ndgroups;
+            const long waves = (ctas + slots - 1) / slots;
+            // the last wave rarely runs full length: count it in proportion to its fill, but never below half a wave
+            const long rem = ctas - (waves - 1) * slots;
+            const double last = rem >= slots ? 1.0 : (0.5 + 0.5 * (double)rem / (double)slots);
+            const long cost = (long)(((double)(waves - 1) + last) * (rows + 11) * 16);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_ns = ns; best_rows = rows; }
+        }
+    }
     P.remap_sms = 0; P.remap_ctas = 0;
     if (c->cvf_remap) {
         int nsm = 0;
@@ -250,8 +268,8 @@ int launch_cvf_stream(psm_ctx* c)
         P.remap_ctas = (int)((227 * 1024) / ((size_t)8 * 4 * nthreads * sizeof(float4) + 1024));  // resident CTAs by shared memory
         if (P.remap_ctas * nthreads * 170 > 65536) P.remap_ctas = 65536 / (nthreads * 170);      // ... and by registers
     }
-    if (c->cvf_target_rows > 0) target_rows = c->cvf_target_rows;
-    plan_segments(c->H, target_rows, &P.nseg, &P.seg_rows);
+    P.nseg = best_ns; P.seg_rows = best_rows;
+    if (c->cvf_target_rows > 0) plan_segments(c->H, c->cvf_target_rows, &P.nseg, &P.seg_rows);
     // kernel selection: mode (exact / mixed) x tuning variant (PSM option 100)
     //   variant 0 (shipped): integer widening + history ring in tensor memory (+ L1 prefetch of the next guide rows in exact mode)
     //   variant 1: F2F conversions, ring in shared memory (the round-1 kernel, kept as the A/B baseline; exact only)
@@ -747,6 +765,9 @@ int psm_p2p_create_buffer(psm_ctx* c, int nranks, void** d_buffer)
     if (int rc = bind(c)) return rc;
     if (nranks < 1 || nranks > kMaxRanks || !d_buffer) return fail(c, PSM_EINVAL, "bad nranks %d (1..%d)", nranks, kMaxRanks);
     if (c->p2p_own) { cudaFree(c->p2p_own); c->p2p_own = nullptr; }
+    for (int i = 0; i < c->p2p_nimported; ++i) cudaIpcCloseMemHandle(c->p2p_imported[i]);   // peers of a previous exchange set-up
+    c->p2p_nimported = 0;
+    for (int r = 0; r < kMaxRanks; ++r) c->p2p_peer[r] = nullptr;
     const size_t kb = p2p_keys_bytes(c, nranks), mb = p2p_maps_bytes(c), fb = p2p_flags_bytes();
     PSM_CUDA(c, cudaMalloc(&c->p2p_own, kb + mb + fb));
     PSM_CUDA(c, cudaMemsetAsync(c->p2p_own, 0xff, kb + mb, c->stream));
@@ -756,6 +777,7 @@ int psm_p2p_create_buffer(psm_ctx* c, int nranks, void** d_buffer)
     PSM_CUDA(c, cudaStreamSynchronize(c->stream));
     c->p2p_nranks = nranks;
     c->p2p_seq = 0;
+    c->p2p_waited_seq = 0;
     *d_buffer = c->p2p_own;
     return PSM_OK;
 }
@@ -837,14 +859,19 @@ int psm_disp_reduce_p2p(psm_ctx* c)
         chunk_reduce_kernel<<<(peers.chunk + 255) / 256, 256, 0, c->stream>>>(peers, npix);
         PSM_LAUNCH_CHECK(c);
     }
-    if (c->p2p_sync) {  // local maps complete + every reducer done with this rank's keys
-        for (int v = 0; v < 2; ++v) {
-            P2pPeers peers;
-            p2p_fill(c, v, peers);
-            p2p_wait_done_kernel<<<1, 32, 0, c->stream>>>(peers.flags[c->p2p_rank], c->p2p_nranks, c->p2p_seq);
-            PSM_LAUNCH_CHECK(c);
-        }
-    }
+    return PSM_OK;
+}
+
+// the local result maps are complete once every rank's DONE flag carries this frame's number: enqueue the wait in front
+// of a consumer of the maps (once per frame)
+static int p2p_wait_done(psm_ctx* c)
+{
+    if (!c->p2p_sync || c->p2p_waited_seq == c->p2p_seq) return PSM_OK;
+    P2pPeers peers;
+    p2p_fill(c, 0, peers);
+    p2p_wait_done_kernel<<<1, 32, 0, c->stream>>>(peers.flags[c->p2p_rank], c->p2p_nranks, c->p2p_seq);
+    PSM_LAUNCH_CHECK(c);
+    c->p2p_waited_seq = c->p2p_seq;
     return PSM_OK;
 }
 
@@ -852,6 +879,7 @@ int psm_disp_fetch_p2p(psm_ctx* c, uint8_t* left, size_t left_step, uint8_t* rig
 {
     if (int rc = bind(c)) return rc;
     if (!c->p2p_own) return fail(c, PSM_ESTATE, "no exchange block");
+    if (int rc = p2p_wait_done(c)) return rc;
     const unsigned char* maps = c->p2p_own + p2p_keys_bytes(c, c->p2p_nranks);
     if (int rc = copy_map_out(c, maps, left, left_step)) return rc;
     if (int rc = copy_map_out(c, maps + (size_t)c->W * c->H, right, right_step)) return rc;
@@ -887,6 +915,8 @@ int psm_post_process_device(psm_ctx* c)
         PSM_CUDA(c, cudaMalloc(&c->pp_packed, npix * sizeof(uint32_t)));
         for (int v = 0; v < 2; ++v) PSM_CUDA(c, cudaMalloc(&c->dis_pp[v], npix));
     }
+    if (c->p2p_own && c->p2p_seq > 0)
+        if (int rc = p2p_wait_done(c)) return rc;
     if (int rc = stage_begin(c, 5)) return rc;
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);

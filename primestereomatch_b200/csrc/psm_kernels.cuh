@@ -506,8 +506,9 @@ __global__ void __launch_bounds__(256) wta_kernel(const float* __restrict__ vol,
 //                        the min over the nranks slots of its chunk, stores the winning disparity (u8)
 //                        into EVERY rank's result map -- reduce + gather in one kernel -- and its last CTA
 //                        raises this rank's DONE flag in every peer's block;
-//   p2p_wait_done_kernel: one thread spins until all ranks' DONE flags carry this frame's sequence number;
-//                        after it the local result maps are complete and the key slots may be overwritten.
+//   p2p_wait_done_kernel: spins until all ranks' DONE flags carry this frame's sequence number; after it the local result
+//                        maps are complete.  Launched only in front of a consumer of the maps (D2H fetch, post-filter);
+//                        the NEXT frame's scatter kernel does the same wait itself before it overwrites the key slots.
 // Flags are monotonically increasing frame sequence numbers (never reset), written with release and read
 // with acquire semantics at system scope, so the exchange needs NO library collective or host barrier:
 // a waiting kernel only ever waits for kernels of other GPUs that do not wait for it.
@@ -551,6 +552,13 @@ __device__ __forceinline__ void p2p_publish(const P2pPeers& peers, int flag_offs
 __global__ void __launch_bounds__(256) wta_scatter_kernel(const float* __restrict__ vol, int W, int H, int Wp, int d_begin, int d_count,
                                                           P2pPeers peers)
 {
+    if (peers.seq > 1) {   // the key slots written below were read by the reducers of the PREVIOUS frame: wait for their DONE flags
+        if (threadIdx.x < (unsigned)peers.nranks) {
+            const unsigned* f = peers.flags[peers.rank] + kMaxRanks + threadIdx.x;
+            while ((int)(ld_acquire_sys(f) - (peers.seq - 1)) < 0) __nanosleep(64);
+        }
+        __syncthreads();
+    }
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
     const bool active = x4 < W;  // inactive lanes still take part in the staged store below
@@ -615,10 +623,11 @@ __global__ void __launch_bounds__(256) chunk_reduce_kernel(P2pPeers peers, unsig
     if (peers.seq) p2p_publish(peers, kMaxRanks);   // DONE
 }
 
-__global__ void p2p_wait_done_kernel(const unsigned* flags /* this rank's flag words of one view */, int nranks, unsigned seq)
+__global__ void p2p_wait_done_kernel(const unsigned* flags /* this rank's flag words: [2 views][2 * kMaxRanks] */, int nranks, unsigned seq)
 {
-    if (threadIdx.x < (unsigned)nranks) {
-        const unsigned* f = flags + kMaxRanks + threadIdx.x;
+    if (threadIdx.x < 2u * (unsigned)nranks) {
+        const unsigned view = threadIdx.x / nranks, r = threadIdx.x - view * nranks;
+        const unsigned* f = flags + view * 2 * kMaxRanks + kMaxRanks + r;
         while ((int)(ld_acquire_sys(f) - seq) < 0) __nanosleep(64);
     }
 }
