@@ -841,7 +841,7 @@ int psm_disp_select_keys_p2p(psm_ctx* c)
     for (int v = 0; v < 2; ++v) {
         P2pPeers peers;
         p2p_fill(c, v, peers);
-        dim3 blk(256), grd(((c->W + 3) / 4 + 255) / 256, c->H);
+        dim3 blk(256), grd(((c->W + 3) / 4 + 255) / 256, (c->H + kScatterRows - 1) / kScatterRows);
         wta_scatter_kernel<<<grd, blk, 0, c->stream>>>(c->vol[v], c->W, c->H, c->Wp, c->d_begin, c->d_count, peers);
         PSM_LAUNCH_CHECK(c);
     }

@@ -513,6 +513,7 @@ __global__ void __launch_bounds__(256) wta_kernel(const float* __restrict__ vol,
 // with acquire semantics at system scope, so the exchange needs NO library collective or host barrier:
 // a waiting kernel only ever waits for kernels of other GPUs that do not wait for it.
 constexpr int kMaxRanks = 8;
+constexpr int kScatterRows = 4;   // image rows per CTA of wta_scatter_kernel
 
 struct P2pPeers {
     unsigned long long* keys[kMaxRanks];  // per rank: exchange block of this view  [nranks][chunk]
@@ -560,40 +561,43 @@ __global__ void __launch_bounds__(256) wta_scatter_kernel(const float* __restric
         __syncthreads();
     }
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y;
     const bool active = x4 < W;  // inactive lanes still take part in the staged store below
     const size_t plane = (size_t)H * Wp;
-    const float* p = vol + (size_t)y * Wp + (active ? x4 : 0);
-    float mc[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-    int md[4] = {0, 0, 0, 0};
-    int dl = (d_begin == 0) ? 1 : 0;
-#pragma unroll 8
-    for (; active && dl < d_count; ++dl) {
-        const float4 c = __ldg(reinterpret_cast<const float4*>(p + (size_t)dl * plane));
-        const int d = d_begin + dl;
-        if (c.x < mc[0]) { mc[0] = c.x; md[0] = d; }
-        if (c.y < mc[1]) { mc[1] = c.y; md[1] = d; }
-        if (c.z < mc[2]) { mc[2] = c.z; md[2] = d; }
-        if (c.w < mc[3]) { mc[3] = c.w; md[3] = d; }
-    }
     // Stage the warp's 128 keys in shared memory and send them out lane-contiguously: every store
     // instruction then writes 32 consecutive keys (256 contiguous bytes, whole 32-byte sectors) to
     // one peer, instead of 32 lanes x 8 bytes at a 32-byte stride (partial sectors over NVLink).
     __shared__ unsigned long long stage[8][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // a CTA handles kScatterRows consecutive rows: four times fewer CTAs have to fence and count in p2p_publish
+    for (int y = blockIdx.y * kScatterRows; y < min(H, (int)(blockIdx.y + 1) * kScatterRows); ++y) {
+        const float* p = vol + (size_t)y * Wp + (active ? x4 : 0);
+        float mc[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+        int md[4] = {0, 0, 0, 0};
+        int dl = (d_begin == 0) ? 1 : 0;
+#pragma unroll 8
+        for (; active && dl < d_count; ++dl) {
+            const float4 c = __ldg(reinterpret_cast<const float4*>(p + (size_t)dl * plane));
+            const int d = d_begin + dl;
+            if (c.x < mc[0]) { mc[0] = c.x; md[0] = d; }
+            if (c.y < mc[1]) { mc[1] = c.y; md[1] = d; }
+            if (c.z < mc[2]) { mc[2] = c.z; md[2] = d; }
+            if (c.w < mc[3]) { mc[3] = c.w; md[3] = d; }
+        }
+        __syncwarp();   // the previous row's staged keys have been sent
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        stage[warp][4 * lane + j] = ((unsigned long long)float_order_key(mc[j]) << 32) | (unsigned)md[j];
-    __syncwarp();
-    const int xw = x4 - 4 * lane;  // first column of this warp
+        for (int j = 0; j < 4; ++j)
+            stage[warp][4 * lane + j] = ((unsigned long long)float_order_key(mc[j]) << 32) | (unsigned)md[j];
+        __syncwarp();
+        const int xw = x4 - 4 * lane;  // first column of this warp
 #pragma unroll
-    for (int s4 = 0; s4 < 4; ++s4) {
-        const int idx = 32 * s4 + lane;
-        const int x = xw + idx;
-        if (x < W) {
-            const unsigned pix = (unsigned)y * (unsigned)W + (unsigned)x;
-            const unsigned owner = pix / peers.chunk;
-            peers.keys[owner][(size_t)peers.rank * peers.chunk + (pix - owner * peers.chunk)] = stage[warp][idx];  // peer (or own) memory
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const int idx = 32 * s4 + lane;
+            const int x = xw + idx;
+            if (x < W) {
+                const unsigned pix = (unsigned)y * (unsigned)W + (unsigned)x;
+                const unsigned owner = pix / peers.chunk;
+                peers.keys[owner][(size_t)peers.rank * peers.chunk + (pix - owner * peers.chunk)] = stage[warp][idx];  // peer (or own) memory
+            }
         }
     }
     if (peers.seq) p2p_publish(peers, 0);   // ARRIVE

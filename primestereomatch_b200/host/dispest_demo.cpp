@@ -1,6 +1,6 @@
 // dispest_demo.cpp -- drives the C++ DispEst facade exactly like StereoMatch::compute does
 // (reference src/StereoMatch.cpp:198-241): setInputImages -> CostConst_GPU -> CostFilter_GPU ->
-// DispSelect_GPU.  Raw I/O so it needs no image library:
+// DispSelect_GPU -> PostProcess_GPU.  Raw I/O so it needs no image library:
 //   dispest_demo W H D left.f32 right.f32 out_left.u8 out_right.u8
 #include <cstdio>
 #include <vector>
@@ -32,7 +32,7 @@ int main(int argc, char** argv)
     if (!rc) rc = SMDE->DispSelect_GPU();
     if (!rc) rc = SMDE->PostProcess_GPU();
     if (rc) { std::fprintf(stderr, "stage failed (%d): %s\n", rc, SMDE->last_error()); return 1; }
-    std::printf("CVC %.3f ms  CVF %.3f ms  DispSel %.3f ms\n", SMDE->stage_ms(1), SMDE->stage_ms(2), SMDE->stage_ms(3));
+    std::printf("CVC %.3f ms  CVF %.3f ms  DispSel %.3f ms  PP %.3f ms\n", SMDE->stage_ms(1), SMDE->stage_ms(2), SMDE->stage_ms(3), SMDE->stage_ms(5));
     FILE* f = std::fopen(argv[6], "wb"); std::fwrite(SMDE->lDisMap.data, 1, (size_t)W * H, f); std::fclose(f);
     f = std::fopen(argv[7], "wb"); std::fwrite(SMDE->rDisMap.data, 1, (size_t)W * H, f); std::fclose(f);
     delete SMDE;

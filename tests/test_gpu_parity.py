@@ -263,9 +263,10 @@ def test_sharded_keys_match_unsharded(scenes, oracle_scene_results):
             de.close()
 
 
-def test_cpp_dispest_facade_demo(tmp_path, scenes, oracle_scene_results):
+def test_cpp_dispest_facade_demo(tmp_path, scenes, oracle, oracle_scene_results):
     """The C++ DispEst facade (primestereomatch_b200/host), driven like StereoMatch::compute drives the
-    reference's DispEst, produces the oracle's maps on Teddy."""
+    reference's DispEst (CostConst_GPU, CostFilter_GPU, DispSelect_GPU, PostProcess_GPU), produces the oracle's
+    post-filtered maps on Teddy."""
     import subprocess
     from conftest import ROOT
     exe = os.path.join(ROOT, "primestereomatch_b200", "host", "dispest_demo")
@@ -279,8 +280,8 @@ def test_cpp_dispest_facade_demo(tmp_path, scenes, oracle_scene_results):
     assert out.returncode == 0, out.stderr
     ld = np.fromfile(tmp_path / "l.u8", np.uint8).reshape(H, W)
     rd = np.fromfile(tmp_path / "r.u8", np.uint8).reshape(H, W)
-    assert_same(ld, oracle_scene_results["Teddy"]["ld"], "C++ facade lDisMap")
-    assert_same(rd, oracle_scene_results["Teddy"]["rd"], "C++ facade rDisMap")
+    assert_same(ld, oracle.post_process(l, oracle_scene_results["Teddy"]["ld"]), "C++ facade lDisMap (after PostProcess_GPU)")
+    assert_same(rd, oracle.post_process(r, oracle_scene_results["Teddy"]["rd"]), "C++ facade rDisMap (after PostProcess_GPU)")
 
 
 def test_fused_wta_p2p_gather_matches_unsharded(scenes, oracle_scene_results):
