@@ -24,9 +24,15 @@
  *   psm_read_cost_slice   <-> DispEst::printCV (cost-slice dump) src/DispEst.cpp:181-194
  *   psm_stage_ms          <-> cvc_time/cvf_time/dispsel_time     src/StereoMatch.cpp:209-241
  *
- * Numerics contract: results equal the reference's pthreads CPU path
- * (src/CVC.cpp, src/CVF.cpp, src/DispSel.cpp), NOT the divergent OpenCL kernels
- * (SURVEY.md section 2.1).  See DESIGN.md.
+ * Numerics contract: results equal the reference's CPU building blocks src/CVC.cpp, src/CVF.cpp (GuidedFilter_cv, the
+ * full-resolution guided filter) and src/DispSel.cpp bit for bit -- NOT the divergent OpenCL kernels (SURVEY.md section
+ * 2.1), and NOT what the reference binary's CPU mode runs today: StereoMatch::compute calls CostFilter_FGF (the
+ * sub-sampled Fast Guided Filter) because the CostFilter_CPU that would call GuidedFilter_cv is declared but never
+ * defined; that branch is psm_cost_filter_fgf.  "Bit for bit" for the box filters means: fp64 sums of 64 floats are
+ * exact -- and therefore independent of summation order -- unless a window spans more than 2^23 in magnitude; beyond that
+ * OpenCV's order and this library's round differently in fp64 and the final float can differ in its last bit with
+ * probability ~2^-28 per mean (never observed).  PSM_CVF_MIXED trades the bit-exact q for speed inside the tolerance
+ * the task states (a, b bit-exact, |dq| <= 4e-6 on O(1) costs).  See DESIGN.md.
  *
  * Threading: one psm_ctx must not be used concurrently; it may be used from different
  * host threads over its life (every call binds its CUDA device first), matching how the

@@ -131,3 +131,63 @@ def test_full_size_c3_bit_exact(oracle):
     assert_same(g["rf"], ref["rVol"], "C3 right filtered volume")
     assert_same(g["ld"], ref["lDis"], "C3 lDisMap")
     assert_same(g["rd"], ref["rDis"], "C3 rDisMap")
+
+
+def test_async_upload_pipeline_matches_synchronous_calls(scenes, oracle_scene_results):
+    """psm_set_images_async / _commit + psm_disp_select_async (two-deep pipeline: frame k+1 uploads while frame k
+    computes) give the same maps as the synchronous reference-style calls, for alternating frames and for u8 frames."""
+    import ctypes as C
+    torch = pytest.importorskip("torch")
+    l8, r8, l, r = scenes["Teddy"]
+    H, W, _ = l.shape
+    L = capi.lib()
+    frames = [(torch.from_numpy(l).pin_memory(), torch.from_numpy(r).pin_memory()),
+              (torch.from_numpy(r).pin_memory(), torch.from_numpy(l).pin_memory())]   # second frame: views swapped
+    want = []
+    with DispEst(l, r, 64) as de:
+        for fl, fr in frames:
+            de.setInputImages(fl.numpy(), fr.numpy())
+            de.CostConst_GPU(); de.CostFilter_GPU(); de.DispSelect_GPU()
+            want.append((de.lDisMap.copy(), de.rDisMap.copy()))
+        assert np.array_equal(want[0][0], oracle_scene_results["Teddy"]["ld"])
+        maps = [(torch.empty((H, W), dtype=torch.uint8).pin_memory(), torch.empty((H, W), dtype=torch.uint8).pin_memory()) for _ in range(4)]
+        order = [0, 1, 1, 0]
+        step = W * 3 * 4
+        assert L.psm_set_images_commit(de.handle) == capi.PSM_ESTATE            # nothing pending
+        capi.check(L.psm_set_images_async(de.handle, frames[order[0]][0].data_ptr(), step, frames[order[0]][1].data_ptr(), step), de.handle)
+        assert L.psm_set_images_async(de.handle, frames[0][0].data_ptr(), step, frames[0][1].data_ptr(), step) == capi.PSM_ESTATE   # one in flight
+        for k in range(4):
+            capi.check(L.psm_set_images_commit(de.handle), de.handle)
+            if k + 1 < 4:
+                nxt = frames[order[k + 1]]
+                capi.check(L.psm_set_images_async(de.handle, nxt[0].data_ptr(), step, nxt[1].data_ptr(), step), de.handle)
+            capi.check(L.psm_cost_const(de.handle), de.handle)
+            capi.check(L.psm_cost_filter(de.handle), de.handle)
+            capi.check(L.psm_disp_select_async(de.handle, maps[k][0].data_ptr(), W, maps[k][1].data_ptr(), W), de.handle)
+        de.sync()
+        for k in range(4):
+            assert_same(maps[k][0].numpy(), want[order[k]][0], f"pipelined frame {k} lDisMap")
+            assert_same(maps[k][1].numpy(), want[order[k]][1], f"pipelined frame {k} rDisMap")
+        # 8-bit frames through the same pipeline
+        l8p, r8p = torch.from_numpy(l8).pin_memory(), torch.from_numpy(r8).pin_memory()
+        capi.check(L.psm_set_images_u8_async(de.handle, l8p.data_ptr(), W * 3, r8p.data_ptr(), W * 3), de.handle)
+        capi.check(L.psm_set_images_commit(de.handle), de.handle)
+        capi.check(L.psm_cost_const(de.handle), de.handle)
+        capi.check(L.psm_cost_filter(de.handle), de.handle)
+        capi.check(L.psm_disp_select_async(de.handle, maps[0][0].data_ptr(), W, maps[0][1].data_ptr(), W), de.handle)
+        de.sync()
+        assert_same(maps[0][0].numpy(), want[0][0], "u8 pipelined lDisMap")
+
+
+def test_selection_requires_a_filtered_volume():
+    """the select entry points used to run on zero / raw volumes when called out of order."""
+    l = np.random.default_rng(0).random((32, 48, 3), dtype=np.float32)
+    with DispEst(l, l, 8) as de:
+        L = capi.lib()
+        assert L.psm_disp_select_device(de.handle) == capi.PSM_ESTATE          # nothing computed yet
+        de.CostConst_GPU()
+        assert L.psm_disp_select_device(de.handle) == capi.PSM_ESTATE          # raw costs only
+        de.CostFilter_GPU()
+        assert L.psm_disp_select_device(de.handle) == capi.PSM_OK
+        de.CostConst_GPU()
+        assert L.psm_disp_select_device(de.handle) == capi.PSM_ESTATE          # a new CVC invalidates the filtered volume

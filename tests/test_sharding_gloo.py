@@ -85,3 +85,15 @@ def test_two_rank_key_exchange_matches_wta():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_band_rows_partition_the_image():
+    from primestereomatch_b200.sharding import band_rows
+    for H in (1, 7, 375, 1080):
+        for world in (1, 2, 3, 8):
+            covered = []
+            for r in range(world):
+                r0, r1, rows = band_rows(H, world, r)
+                assert 0 <= r0 <= r1 <= H and r1 - r0 <= rows
+                covered += list(range(r0, r1))
+            assert covered == list(range(H))
