@@ -65,4 +65,29 @@ __device__ __forceinline__ uint32_t float_order_key(float c)
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// (shared by the guide precompute and the streaming guided filter; the derivation is at the top of psm_cvf_stream.cuh)
+// ---- widening into the 2^-896-scaled fp64 domain --------------------------------------------
+constexpr double kScaleDown = 0x1p-896;   // what the integer widening multiplies by
+constexpr double kMeanScaled = 0x1p890;   // 2^896 / 64
+constexpr double kMeanPlain = 0x1p-6;     // 1 / 64
+
+// non-negative finite float (zero / denormal included): one IMAD.WIDE.U32
+__device__ __forceinline__ double widen_nn(float f)
+{
+    unsigned long long r;
+    asm("mul.wide.u32 %0, %1, 0x20000000;" : "=l"(r) : "r"(__float_as_uint(f)));
+    return __longlong_as_double((long long)r);
+}
+// any finite float: shift the sign out, widen, put the sign back
+__device__ __forceinline__ double widen_sg(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    unsigned long long r;
+    asm("mul.wide.u32 %0, %1, 0x10000000;" : "=l"(r) : "r"(u + u));
+    const unsigned hi = (unsigned)(r >> 32) | (u & 0x80000000u);
+    return __hiloint2double((int)hi, (int)(unsigned)r);
+}
+// anything (slow path): conversion pipe + exact rescale
+__device__ __forceinline__ double widen_any(float f) { return __dmul_rn((double)f, kScaleDown); }
+
 }  // namespace psm

@@ -239,13 +239,21 @@ __global__ void __launch_bounds__(128) fgf_up_kernel(float* __restrict__ vol, si
         i2[0] = c.x; i2[1] = c.y; i2[2] = c.z; i2[3] = c.w;
     }
     float q[4];
+    int c0 = -1, c1 = -1;
+    float4 s00 = make_float4(0.f, 0.f, 0.f, 0.f), s01 = s00, s10 = s00, s11 = s00;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int x = x4 + j;
         if (x >= g.W) { q[j] = 0.f; continue; }
         const FgfTap tx = pl.x[x];
         const float fx = tx.f, a0 = fsub(1.f, fx);
-        const float4 s00 = __ldg(row0 + tx.i0), s01 = __ldg(row0 + tx.i1), s10 = __ldg(row1 + tx.i0), s11 = __ldg(row1 + tx.i1);
+        // consecutive pixels share their low-res column pair (s >= 2) or shift it by one: reload only what changed
+        if (tx.i0 != c0 || tx.i1 != c1) {
+            if (tx.i0 == c1) { s00 = s01; s10 = s11; }
+            else { s00 = __ldg(row0 + tx.i0); s10 = __ldg(row1 + tx.i0); }
+            s01 = __ldg(row0 + tx.i1); s11 = __ldg(row1 + tx.i1);
+            c0 = tx.i0; c1 = tx.i1;
+        }
         // rows after columns, like cv::resize: h = S0*(1-fx) + S1*fx per source row, then h0*(1-fy) + h1*fy
 #define PSM_FGF_UP(c) fadd(fmul(fadd(fmul(s00.c, a0), fmul(s01.c, fx)), b0), fmul(fadd(fmul(s10.c, a0), fmul(s11.c, fx)), fy))
         const float ur = PSM_FGF_UP(x), ug = PSM_FGF_UP(y), ub = PSM_FGF_UP(z), ubb = PSM_FGF_UP(w);

@@ -72,9 +72,10 @@ __global__ void ingest_kernel(const T* __restrict__ src, size_t step_bytes, int 
     I0[o] = v0;
     I1[o] = v1;
     I2[o] = v2;
-    // the CVF kernel's integer widening assumes I >= +0 and finite (images are in [0,1] by contract,
-    // DispEst data contract SURVEY 8b); anything else raises the per-view flag and selects its slow path
-    if (max(max(__float_as_uint(v0), __float_as_uint(v1)), __float_as_uint(v2)) >= 0x7f800000u) atomicOr(guide_flag, 1);
+    // the integer widening in guide_kernel / the CVF kernel assumes I >= +0, finite, and I * I finite (images are in
+    // [0,1] by contract, DispEst data contract SURVEY 8b); a negative, non-finite or >= 2^63 value raises the per-view
+    // flag and selects their conversion-pipe paths (bit patterns compare like the magnitudes; the sign bit sorts last)
+    if (max(max(__float_as_uint(v0), __float_as_uint(v1)), __float_as_uint(v2)) >= 0x5f000000u) atomicOr(guide_flag, 1);
     const float gr = gray_at(row, reflect101(x + 1, W), gray_mode);
     const float gl = gray_at(row, reflect101(x - 1, W), gray_mode);
     grd[o] = fsub(gr, gl);
@@ -328,6 +329,11 @@ __global__ void __launch_bounds__(128) guide_kernel(const GuideParams P)
 #pragma unroll
         for (int j = 0; j < 4; ++j) V[k][j] = 0.0;
 
+    // f32 -> f64 as in the streaming filter (psm_cvf_stream.cuh): image values and their products are non-negative, so
+    // bits(u) * 2^29 is the double f * 2^-896 (one IMAD.WIDE.U32 instead of an F2F); the sums stay in that scaled domain
+    // and the scale is folded into the final multiply.  A guide flagged by ingest_kernel (negative / non-finite image
+    // values) converts with F2F and rescales instead.
+    const bool fastw = (P.guide_flags[view] & 1) == 0;   // bit 0 is final before this launch (bit 1 is raised below)
     auto feed = [&](int r, const bool add) {
         const size_t ro = (size_t)reflect101(r, H) * Wp + cin;
         float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4, c4 = a4;
@@ -341,7 +347,10 @@ __global__ void __launch_bounds__(128) guide_kernel(const GuideParams P)
             const float a = comp(a4, j), b = comp(b4, j), c = comp(c4, j);
             const float t[9] = {a, b, c, fmul(a, a), fmul(a, b), fmul(a, c), fmul(b, b), fmul(b, c), fmul(c, c)};  // CVF.cpp:62
 #pragma unroll
-            for (int k = 0; k < 9; ++k) V[k][j] = add ? __dadd_rn(V[k][j], (double)t[k]) : __dsub_rn(V[k][j], (double)t[k]);
+            for (int k = 0; k < 9; ++k) {
+                const double w = fastw ? widen_nn(t[k]) : widen_any(t[k]);
+                V[k][j] = add ? __dadd_rn(V[k][j], w) : __dsub_rn(V[k][j], w);
+            }
         }
     };
 
@@ -354,7 +363,7 @@ __global__ void __launch_bounds__(128) guide_kernel(const GuideParams P)
             double h[4];
             hsum8(V[k], h);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) m[k][j] = (float)__dmul_rn(h[j], 1.0 / 64.0);
+            for (int j = 0; j < 4; ++j) m[k][j] = (float)__dmul_rn(h[j], kMeanScaled);
         }
         feed(y - kBoxAnchor, false);
         float o[16][4];  // planes kGuideMean .. kGuidePlanes-1

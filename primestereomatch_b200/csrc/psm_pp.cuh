@@ -17,9 +17,9 @@
 // B200 mapping (nothing like the reference's serial column scan with necklace tables): one WARP per pixel,
 //   the 361 window taps dealt round-robin to the 32 lanes (12 rounds), each tap one 4-byte load of a packed
 //   u32 image (disparity << 24 | R6 << 16 | G6 << 8 | B6);
-//   per round the lanes holding the same disparity combine their weights (__match_any_sync + __reduce_add_sync) and one
-//   lane adds the sum to a 256-bin histogram in shared memory (1 KB per warp): integer sums, order-independent;
-//   then each lane scans 8 bins, a warp prefix sum finds the first bin where 2*cum >= total.
+//   the taps ((disparity, fixed-point weight) pairs) stay in registers, 12 per lane; the weighted median is found by eight
+//   bisection steps on the value, each a masked add per tap and one warp REDUX -- no shared memory, no atomics, integer
+//   sums (exact, order-independent, identical to a 256-bin histogram scan).
 #pragma once
 #include "psm_common.cuh"
 
@@ -28,6 +28,9 @@ namespace psm {
 constexpr int kPpRadius = 9;                 // MED_SZ / 2, reference include/PP.h:12
 constexpr int kPpMaxD2 = 3 * 63 * 63;        // largest squared distance between two 6-bit colours
 constexpr int kPpWarps = 8;                  // warps (pixels in flight) per CTA
+constexpr int kPpLutN = 1344;                // the 2^-22 fixed-point weight is zero beyond d2 = 1295 (exp(-d2/81.3) < 2^-23): only this
+                                             // prefix of the table is ever non-zero; it lives in shared memory (random gathers: bank
+                                             // conflicts cost a few cycles, L1 line wavefronts cost up to 32 per load)
 
 // guide planes (float, BGR planar) + u8 disparity map -> packed u32 image
 __global__ void pp_pack_kernel(const float* __restrict__ I0, const float* __restrict__ I1, const float* __restrict__ I2, int Wp,
@@ -50,66 +53,50 @@ __global__ void pp_pack_kernel(const float* __restrict__ I0, const float* __rest
 __global__ void __launch_bounds__(kPpWarps * 32) pp_wmf_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ lut,
                                                               int W, int H, uint8_t* __restrict__ out)
 {
-    __shared__ uint32_t hist[kPpWarps][256];
+    __shared__ uint32_t slut[kPpLutN];
+    for (int i = threadIdx.x; i < kPpLutN; i += blockDim.x) slut[i] = __ldg(lut + i);
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* h = hist[warp];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) h[lane * 8 + k] = 0;
-    __syncwarp();
+    constexpr int kSide = 2 * kPpRadius + 1, kTaps = kSide * kSide, kRounds = (kTaps + 31) / 32;
     const long npix = (long)W * H;
     for (long pix = (long)blockIdx.x * kPpWarps + warp; pix < npix; pix += (long)gridDim.x * kPpWarps) {
         const int y = (int)(pix / W), x = (int)(pix - (long)y * W);
         const uint32_t cp = __ldg(packed + pix);
         const int pb = cp & 63, pg = (cp >> 8) & 63, pr = (cp >> 16) & 63;
+        // the 361 window taps are dealt round-robin to the 32 lanes and stay in registers: (disparity, weight) x 12
+        uint32_t dq[kRounds], wq[kRounds];
         uint32_t total = 0;
-        constexpr int kSide = 2 * kPpRadius + 1, kTaps = kSide * kSide;
-        // the 361 window taps are dealt to the 32 lanes round-robin (12 rounds); a lane's tap is (i / 19, i % 19)
-        for (int base = 0; base < kTaps; base += 32) {
-            const int i = base + lane;
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            const int i = r * 32 + lane;
             const int dy = i / kSide, dx = i - dy * kSide;
             const int yy = y - kPpRadius + dy, xx = x - kPpRadius + dx;
             const bool ok = i < kTaps && yy >= 0 && yy < H && xx >= 0 && xx < W;
-            uint32_t w = 0;
-            unsigned dq = 0x100u + lane;      // a key no valid tap has
+            dq[r] = 256u;     // greater than every candidate value: never counted
+            wq[r] = 0u;
             if (ok) {
                 const uint32_t cq = __ldg(packed + (size_t)yy * W + xx);
                 const int d0 = pb - (int)(cq & 63), d1 = pg - (int)((cq >> 8) & 63), d2 = pr - (int)((cq >> 16) & 63);
-                w = __ldg(lut + (d0 * d0 + d1 * d1 + d2 * d2));
-                dq = cq >> 24;
+                const int dd = d0 * d0 + d1 * d1 + d2 * d2;
+                wq[r] = dd < kPpLutN ? slut[dd] : 0u;
+                dq[r] = cq >> 24;
             }
-            total += w;
-            // combine the taps that carry the same disparity (neighbouring pixels usually do) before touching shared memory:
-            // every lane learns its peer set in one MATCH, the peers add their weights with one REDUX, the lowest peer owns the bin
-            const unsigned peers = __match_any_sync(0xffffffffu, dq);
-            const uint32_t s = __reduce_add_sync(peers, w);
-            if (ok && lane == __ffs(peers) - 1) h[dq] += s;
+            total += wq[r];
         }
-        __syncwarp();
         total = __reduce_add_sync(0xffffffffu, total);
-        // lane l owns bins 8l .. 8l+7
-        uint32_t b8[8], mine = 0;
+        // out = min { v : 2 * sum_{dq <= v} w >= total }: eight bisection steps, each one masked add per tap and one REDUX
+        // (integer sums: exact and order-independent, identical to a histogram scan)
+        int lo = 0, hi = 255;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { b8[k] = h[lane * 8 + k]; mine += b8[k]; h[lane * 8 + k] = 0; }
-        uint32_t incl = mine;
+        for (int it = 0; it < 8; ++it) {
+            const int mid = (lo + hi) >> 1;
+            uint32_t s = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            for (int r = 0; r < kRounds; ++r) s += dq[r] <= (uint32_t)mid ? wq[r] : 0u;
+            s = __reduce_add_sync(0xffffffffu, s);
+            if (2u * s >= total) hi = mid; else lo = mid + 1;
         }
-        // first lane whose inclusive sum reaches half of the total (2*cum >= total; sums < 2^31)
-        const unsigned reach = __ballot_sync(0xffffffffu, 2u * incl >= total);
-        const int first = __ffs(reach) - 1;   // total > 0 (the centre tap has weight 1), so lane 31 always reaches
-        if (lane == first) {
-            uint32_t cum = incl - mine;
-            int v = lane * 8;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                cum += b8[k];
-                if (2u * cum >= total) { v = lane * 8 + k; break; }
-            }
-            out[pix] = (uint8_t)(v > 255 ? 255 : v);
-        }
-        __syncwarp();
+        if (lane == 0) out[pix] = (uint8_t)lo;
     }
 }
 

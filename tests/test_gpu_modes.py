@@ -65,6 +65,26 @@ def test_guide_outside_the_integer_domain(oracle):
     assert_same(g["ld"], ref["lDis"], "lDisMap")
 
 
+@pytest.mark.parametrize("big", [1000.0, 3.0e9, 1.0e19, 2.5e25])
+def test_guide_planes_with_large_values(big, oracle):
+    """The guide precompute widens I and I*I with the integer trick only while every product is finite: values below
+    2^63 stay on that path (1000, 3e9), larger ones (1e19, and 2.5e25 whose square is inf) raise the guide flag and
+    convert with F2F.  Means and variances equal the CPU result either way (NaN == NaN where the CPU has NaN)."""
+    rng = np.random.default_rng(5)
+    H, W = 40, 150
+    l = rng.random((H, W, 3), dtype=np.float32)
+    l[7, 31, 0] = big
+    l[22, 140, 2] = big / 3
+    _, mean, var = oracle.cvf_preprocess(l)
+    with DispEst(l, l, 4) as de:
+        de.CostConst_GPU()
+        with np.errstate(all="ignore"):
+            for c in range(3):
+                assert np.array_equal(de.read_guide_plane(0, 3 + c), mean[c], equal_nan=True), f"mean_I {c}"
+            for k in range(6):
+                assert np.array_equal(de.read_guide_plane(0, 6 + k), var[k], equal_nan=True), f"var_I {k}"
+
+
 @pytest.mark.parametrize("scene", ["Cones", "Teddy"])
 def test_mixed_mode_matches_its_model_and_tolerance(scene, scenes, oracle, oracle_scene_results):
     _, _, l, r = scenes[scene]
