@@ -69,7 +69,7 @@ struct psm_ctx {
     size_t ab_slices = 0;
     cudaEvent_t ev0[kNumStages] = {}, ev1[kNumStages] = {};
     bool ev_valid[kNumStages] = {};
-    int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0, cvf_target_rows = 0, cvf_extra_smem = 0, cvf_threads = 0, cvf_remap = 0;
+    int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0, cvf_target_rows = 0, cvf_extra_smem = 0, cvf_threads = 0, cvf_remap = 0, cvf_no_pack = 0;
     bool have_images = false, guide_valid = false, have_cvc = false, filtered = false;
     uint64_t launches = 0;
     char err[512] = "";
@@ -232,12 +232,26 @@ int launch_cvf_stream(psm_ctx* c)
     for (int v = 0; v < 2; ++v) { P.vol_in[v] = c->vol[v]; P.vol_out[v] = c->vol_alt[v]; P.guide[v] = c->guide[v]; }
     P.W = c->W; P.H = c->H; P.Wp = c->Wp; P.Dloc = c->d_count;
     P.nstrips = (c->W + kStripOut - 1) / kStripOut;
+    // packed remainder strips (psm_cvf_stream.cuh): the columns past the last full strip, 4 or 2 slices per warp.  Needs the
+    // tensor-memory ring and no CTA-level staging (variants 1, 2 and 9 keep the plain decomposition); option 105 = 1 disables.
+    P.pack_gl = 0; P.pack_first = 0; P.pack_ndg = 0; P.pack_x0 = 0;
+    {
+        const bool plain_variant = c->cvf_variant == 9 || c->cvf_variant == 2 || (c->cvf_mode != PSM_CVF_MIXED && c->cvf_variant == 1);
+        const int nfull = c->W / kStripOut, rem = c->W - nfull * kStripOut;
+        if (!c->cvf_no_pack && !plain_variant && !c->cvf_remap && nfull >= 1 && rem > 0) {
+            for (int gl = 8; gl <= 16; gl *= 2) {
+                const int x0 = (c->W - 4 * (gl - 4) + 3) & ~3;
+                if (x0 <= nfull * kStripOut) { P.pack_gl = gl; P.pack_x0 = x0; P.nstrips = nfull; break; }
+            }
+        }
+    }
     // slice-warps per CTA: 3 (4 CTAs per SM) or 4 (3 CTAs per SM) -- the same 12 warps per SM either way; take the one that
     // leaves no warp slot idle in the last slice group (16 slices per rank at 8 GPUs: 4 x 4 instead of 6 x 3 with two idle)
     const int auto_threads = (c->d_count % 3 != 0 && c->d_count % 4 == 0) ? 128 : kCvfThreads;
     const int nthreads = c->cvf_threads > 0 ? c->cvf_threads : auto_threads;
     const int wpc = nthreads / 32;
     P.ndgroups = (c->d_count + wpc - 1) / wpc;
+    if (P.pack_gl) P.pack_ndg = (c->d_count + wpc * (32 / P.pack_gl) - 1) / (wpc * (32 / P.pack_gl));
     // Row segmentation, wave-aware: every segment pays ~11 warm-up rows, and the grid runs in waves of (SMs x resident
     // CTAs) -- with few slices per rank (16 at 8 GPUs) a badly chosen segment count leaves the last wave nearly empty
     // (4 segments: 576 CTAs over 444 slots = 2 waves; 3 segments: 432 CTAs = 1 wave).  Pick the count that minimises
@@ -251,7 +265,7 @@ int launch_cvf_stream(psm_ctx* c)
         for (int want = 1; want <= 12; ++want) {
             int ns = 1, rows = c->H;
             plan_segments(c->H, (c->H + want - 1) / want, &ns, &rows);
-            const long ctas = 2L * ns * P.nstrips * P.ndgroups;
+            const long ctas = 2L * ns * (P.nstrips * P.ndgroups + P.pack_ndg);
             const long waves = (ctas + slots - 1) / slots;
             // the last wave rarely runs full length: count it in proportion to its fill, but never below half a wave
             const long rem = ctas - (waves - 1) * slots;
@@ -320,7 +334,8 @@ int launch_cvf_stream(psm_ctx* c)
         PSM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
     P.guide_flags = c->guide_flags;
     P.one = 1.0f; P.mone = -1.0f;
-    const unsigned grid = 2u * P.nseg * P.nstrips * P.ndgroups;
+    P.pack_first = 2 * P.nseg * P.nstrips * P.ndgroups;
+    const unsigned grid = (unsigned)P.pack_first + 2u * P.nseg * P.pack_ndg;
     kern<<<grid, nthreads, smem, c->stream>>>(P);
     PSM_LAUNCH_CHECK(c);
     return PSM_OK;
@@ -476,6 +491,9 @@ int psm_set_option(psm_ctx* c, int key, int value)
         return PSM_OK;
     case 100:  // streaming-kernel variant selector for tuning experiments
         c->cvf_variant = value;
+        return PSM_OK;
+    case 105:  // tuning: 1 = no packed remainder strips (one warp per slice for the last W % 112 columns, as in round 1)
+        c->cvf_no_pack = value ? 1 : 0;
         return PSM_OK;
     case 104:  // undocumented: block->work remap so that co-resident CTAs are work neighbours (0/1)
         c->cvf_remap = value;

@@ -59,6 +59,12 @@
 // a,b at columns outside [0,W) must be the REFLECTED a,b (cv::boxFilter reflects its input, which
 // for the second stage is a,b) -- not what stage 1 computes there from mirrored p (the 8-wide window
 // is asymmetric) -- so border strips overwrite those entries by lane shuffles.
+// Packed remainder.  W is rarely a multiple of 112 (1920 = 17 x 112 + 16): a whole warp for the last 16 columns of every
+// slice is 1/18 of the kernel's work.  When the remainder needs at most 16 lanes (its columns + 16 halo columns), the
+// regular strips stop at 112 * floor(W / 112) and extra "packed" CTAs filter the remainder of 4 (8-lane groups) or 2
+// (16-lane groups) SLICES per warp: lane -> (slice group, lane in group), everything below is per lane anyway (base
+// pointers, ring, running sums); the shuffles still run over the whole warp and what crosses a group boundary lands in
+// the group's halo lanes, whose results are never stored -- exactly like the first and last lanes of a full strip.
 // Rows: the top of the image uses weights 1,2,2,2,1 for the first window, the bottom feeds three
 // virtual rows from the ring; input rows reflect by index.  These special cases live in
 // generic_step; the bulk of the rows run the steady step, which has no data-dependent control
@@ -87,6 +93,9 @@ struct CvfParams {
     int W, H, Wp, Dloc;
     int nstrips, nseg, seg_rows, ndgroups;
     int remap_sms, remap_ctas;  // SM count and resident CTAs per SM for the block->work remap (0: identity)
+    // packed remainder strips (0 = off): blocks >= pack_first filter the W - nstrips*112 rightmost columns with
+    // 32 / pack_gl slices per warp (pack_gl = 8 or 16 lanes per slice); see "Packed remainder" in the header comment
+    int pack_gl, pack_first, pack_ndg, pack_x0;
     float one, mone;            // +1.0f / -1.0f, passed at run time so that the compiler cannot fold them (packed exact adds, PA)
 };
 
@@ -294,17 +303,30 @@ cvf_stream_kernel(const CvfParams P)
     // share an SM (and its L1) are blockIdx k, k+nsm, k+2nsm, ...; the remap makes those neighbours in
     // work order (consecutive slice groups of the same strip and segment), which read the same guide rows.
     int b = blockIdx.x;
+    const bool packed = P.pack_gl > 0 && b >= P.pack_first;
     if (P.remap_sms > 0) {
         const int per = P.remap_sms * P.remap_ctas;
         const int chunk = b / per, r = b - chunk * per;
         if ((chunk + 1) * per <= (int)gridDim.x) b = chunk * per + (r % P.remap_sms) * P.remap_ctas + r / P.remap_sms;
     }
-    const int dgroup = b % P.ndgroups; b /= P.ndgroups;
-    const int strip = b % P.nstrips;   b /= P.nstrips;
-    const int seg = b % P.nseg;
-    const int view = b / P.nseg;
-    const int dlc_raw = dgroup * wpc + warp;
-    const bool active = dlc_raw < P.Dloc;
+    int dgroup, strip, seg, view;
+    if (packed) {
+        b -= P.pack_first;
+        dgroup = b % P.pack_ndg; b /= P.pack_ndg;
+        strip = P.nstrips;     // the remainder: one past the regular strips
+        seg = b % P.nseg;
+        view = b / P.nseg;
+    } else {
+        dgroup = b % P.ndgroups; b /= P.ndgroups;
+        strip = b % P.nstrips;   b /= P.nstrips;
+        seg = b % P.nseg;
+        view = b / P.nseg;
+    }
+    const int gl = packed ? P.pack_gl : 32;   // lanes per slice
+    const int gln = lane & (gl - 1);          // lane within its slice group
+    const int gbase = lane - gln;
+    const int dlc_raw = packed ? (dgroup * wpc + warp) * (32 / gl) + lane / gl : dgroup * wpc + warp;
+    const bool active = dlc_raw < P.Dloc;     // warp-uniform unless packed
     const int dlc = active ? dlc_raw : P.Dloc - 1;
     constexpr bool ST = (PF == 2);
     const unsigned st_base = (unsigned)__cvta_generic_to_shared(ring);   // staging area (ST): barriers, coefficient stages, image-row ring
@@ -340,8 +362,9 @@ cvf_stream_kernel(const CvfParams P)
     const unsigned Wp = (unsigned)P.Wp;
     const unsigned plane = (unsigned)H * Wp;
     const int out_lo = strip * kStripOut;
-    const int X0 = (strip == P.nstrips - 1 && strip > 0) ? ((W - kStripOut + 3) & ~3) : out_lo;
-    const int cin = X0 - 8 + 4 * lane;
+    const int X0 = packed ? P.pack_x0
+                          : ((P.pack_gl == 0 && strip == P.nstrips - 1 && strip > 0) ? ((W - kStripOut + 3) & ~3) : out_lo);
+    const int cin = X0 - 8 + 4 * gln;
     // per-thread base pointers (bytes); every offset added to them below is warp-uniform
     const char* __restrict__ Gi = reinterpret_cast<const char*>(P.guide[view] + cin);      // guide, input columns
     const char* __restrict__ Ga = reinterpret_cast<const char*>(P.guide[view] + cin + 4);  // guide, a,b columns
@@ -349,7 +372,7 @@ cvf_stream_kernel(const CvfParams P)
     const char* __restrict__ vin = reinterpret_cast<const char*>(P.vol_in[view] + (size_t)dlc * plane + cin);
     char* __restrict__ vout = reinterpret_cast<char*>(P.vol_out[view] + (size_t)dlc * plane + cin + 8);
     const size_t planeB = (size_t)plane * 4, rowB = (size_t)Wp * 4;
-    const bool store_ok = active && lane <= 27 && cin + 8 < W && cin + 8 >= out_lo;
+    const bool store_ok = active && gln <= gl - 5 && cin + 8 < W && cin + 8 >= out_lo;
 
     // a guide with negative / non-finite values (outside the [0,1] image contract) disables the
     // integer widening for the whole launch of this view; `slow` also turns sticky once a row of p
@@ -358,14 +381,14 @@ cvf_stream_kernel(const CvfParams P)
 
     // ---- x-reflection plan for a,b (strips whose a,b columns X0-4 .. X0+115 leave the image) ----
     const bool fix_left = X0 == 0;
-    const bool fix_right = X0 + 115 >= W;
+    const bool fix_right = X0 + 4 * gl - 13 >= W;   // last valid a,b column of the (group's) strip
     int fix_src[4];               // source lane of element j (this lane's a,b column X0-4+4l+j mirrored into the image)
     unsigned maskL = 0, maskR = 0;  // bit j: element j lies left of column 0 / right of column W-1
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int xa = cin + 4 + j;
         const int r = reflect101(xa < -4 ? -4 : (xa > W + 2 ? W + 2 : xa), W) - (X0 - 4);
-        fix_src[j] = (r >> 2) & 31;
+        fix_src[j] = gbase + ((r >> 2) & (gl - 1));
         maskL |= (fix_left && xa < 0) ? (1u << j) : 0u;
         maskR |= (fix_right && xa >= W && xa <= W + 2) ? (1u << j) : 0u;
     }

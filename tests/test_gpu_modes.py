@@ -65,24 +65,47 @@ def test_guide_outside_the_integer_domain(oracle):
     assert_same(g["ld"], ref["lDis"], "lDisMap")
 
 
-@pytest.mark.parametrize("big", [1000.0, 3.0e9, 1.0e19, 2.5e25])
-def test_guide_planes_with_large_values(big, oracle):
-    """The guide precompute widens I and I*I with the integer trick only while every product is finite: values below
-    2^63 stay on that path (1000, 3e9), larger ones (1e19, and 2.5e25 whose square is inf) raise the guide flag and
-    convert with F2F.  Means and variances equal the CPU result either way (NaN == NaN where the CPU has NaN)."""
+# Packed remainder strips (psm_cvf_stream.cuh): the W % 112 rightmost columns are filtered 4 slices per warp (remainder
+# <= 16 columns: 113, 128, 227, 240), 2 slices per warp (<= 48 columns: 129, 160, 260) or by a whole warp per slice
+# (161, 300: the round-1 decomposition, also what option 105 = 1 forces).  D = 5, 9, 13 leave slice groups of the last
+# packed warp without a slice.  Exact: equal to the oracle; mixed: equal to the CPU model of the mode.
+@pytest.mark.parametrize("no_pack", [0, 1])
+@pytest.mark.parametrize("W,H,D", [(113, 30, 5), (128, 26, 9), (129, 40, 4), (160, 33, 13), (161, 24, 5), (227, 31, 6),
+                                   (240, 300, 3), (260, 50, 7), (300, 20, 2)])
+def test_packed_remainder_strips(W, H, D, no_pack, oracle):
+    rng = np.random.default_rng(W * 7 + H)
+    l = rng.random((H, W, 3), dtype=np.float32)
+    r = np.clip(np.roll(l, -2, axis=1) + rng.normal(0, 0.03, (H, W, 3)), 0, 1).astype(np.float32)
+    ref = oracle.pipeline(l, r, D, keep_volumes=True)
+    g = run_gpu(l, r, D, options=[(105, no_pack)])
+    assert_same(g["lf"], ref["lVol"], f"left filtered volume, no_pack={no_pack}")
+    assert_same(g["rf"], ref["rVol"], f"right filtered volume, no_pack={no_pack}")
+    assert_same(g["ld"], ref["lDis"], "lDisMap")
+    assert_same(g["rd"], ref["rDis"], "rDisMap")
+    m = run_gpu(l, r, D, mode=capi.PSM_CVF_MIXED, options=[(105, no_pack)])
+    for img, raw, key in ((l, g["lraw"], "lf"), (r, g["rraw"], "rf")):
+        assert_same(m[key], MM.cost_filter_mixed(oracle, img, raw), f"MIXED {key} vs CPU model, no_pack={no_pack}")
+
+
+@pytest.mark.parametrize("log2_scale", [0, 40, 70])
+def test_guide_planes_with_large_values(log2_scale, oracle):
+    """The guide precompute widens I and I*I with the integer trick only while every product is finite: images below 2^63
+    stay on that path (scale 1 and 2^40), larger ones (scale 2^70: squares overflow to inf) raise the
+    guide flag and convert with F2F.  The image is k/256 * scale, so every fp64 window sum is exact and the comparison does
+    not depend on the summation order; means and variances equal the CPU result (NaN == NaN where the CPU has NaN)."""
     rng = np.random.default_rng(5)
     H, W = 40, 150
-    l = rng.random((H, W, 3), dtype=np.float32)
-    l[7, 31, 0] = big
-    l[22, 140, 2] = big / 3
-    _, mean, var = oracle.cvf_preprocess(l)
-    with DispEst(l, l, 4) as de:
-        de.CostConst_GPU()
-        with np.errstate(all="ignore"):
+    l = (rng.integers(0, 256, (H, W, 3)).astype(np.float32) / 256.0) * np.float32(2.0 ** log2_scale)
+    with np.errstate(all="ignore"):
+        _, mean, var = oracle.cvf_preprocess(l)
+        with DispEst(l, l, 4) as de:
+            de.CostConst_GPU()
             for c in range(3):
                 assert np.array_equal(de.read_guide_plane(0, 3 + c), mean[c], equal_nan=True), f"mean_I {c}"
             for k in range(6):
                 assert np.array_equal(de.read_guide_plane(0, 6 + k), var[k], equal_nan=True), f"var_I {k}"
+    if log2_scale == 70:
+        assert not np.isfinite(var).all()      # the case really left the finite domain
 
 
 @pytest.mark.parametrize("scene", ["Cones", "Teddy"])

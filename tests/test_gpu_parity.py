@@ -16,11 +16,13 @@ pytestmark = pytest.mark.gpu
 A_B_TOL = 1e-4  # north_star: "32-bit float within 1e-4 on a/b"
 
 
-def run_gpu(l, r, D, mode=capi.PSM_CVF_EXACT, variant=0, keep=True):
+def run_gpu(l, r, D, mode=capi.PSM_CVF_EXACT, variant=0, keep=True, options=()):
     out = {}
     with DispEst(l, r, D, 8, True) as de:
         de.set_option(capi.PSM_OPT_CVF_MODE, mode)
         de.set_option(capi.PSM_OPT_VARIANT, variant)
+        for key, value in options:
+            de.set_option(key, value)
         assert de.CostConst_GPU() == 0
         if keep:
             out["lraw"], out["rraw"] = de.read_cost_volume(0), de.read_cost_volume(1)

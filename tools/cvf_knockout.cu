@@ -64,6 +64,7 @@ int main()
     P.ndgroups = (D + wpc - 1) / wpc;
     P.nseg = 4; P.seg_rows = 272;
     P.remap_sms = 0; P.remap_ctas = 0;
+    P.pack_gl = 0; P.pack_first = 0; P.pack_ndg = 0; P.pack_x0 = 0;
     P.one = 1.f; P.mone = -1.f;
     const unsigned grid = 2u * P.nseg * P.nstrips * P.ndgroups;
     const float ex = run<kS2Exact>(P, grid, nthreads, 5);
