@@ -201,6 +201,7 @@ def main():
     ap.add_argument("--extra-smem", type=int, default=0)
     ap.add_argument("--cta-threads", type=int, default=0)
     ap.add_argument("--remap", type=int, default=0)
+    ap.add_argument("--cvc-variant", type=int, default=0, help="CVC kernel build (tuning A/B, option 106)")
     ap.add_argument("--no-pack", type=int, default=0, help="1: one warp per slice for the last W %% 112 columns (tuning A/B)")
     ap.add_argument("--upload", default="banded", choices=["banded", "replicated"],
                     help="N>1, e2e: banded = every rank uploads H/N rows of both images and the bands are "
@@ -252,6 +253,7 @@ def main():
     de.set_option(103, args.cta_threads)
     de.set_option(104, args.remap)
     de.set_option(105, args.no_pack)
+    de.set_option(106, args.cvc_variant)
     stream = torch.cuda.Stream()  # a real (non-default) stream shared by the context and torch's collectives
     torch.cuda.set_stream(stream)
     capi.check(L.psm_set_stream(de.handle, C.c_void_p(stream.cuda_stream)), de.handle)

@@ -69,7 +69,7 @@ struct psm_ctx {
     size_t ab_slices = 0;
     cudaEvent_t ev0[kNumStages] = {}, ev1[kNumStages] = {};
     bool ev_valid[kNumStages] = {};
-    int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0, cvf_target_rows = 0, cvf_extra_smem = 0, cvf_threads = 0, cvf_remap = 0, cvf_no_pack = 0;
+    int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0, cvf_target_rows = 0, cvf_extra_smem = 0, cvf_threads = 0, cvf_remap = 0, cvf_no_pack = 0, cvc_variant = 0;
     bool have_images = false, guide_valid = false, have_cvc = false, filtered = false;
     uint64_t launches = 0;
     char err[512] = "";
@@ -492,6 +492,9 @@ int psm_set_option(psm_ctx* c, int key, int value)
     case 100:  // streaming-kernel variant selector for tuning experiments
         c->cvf_variant = value;
         return PSM_OK;
+    case 106:  // tuning: CVC kernel build (see psm_cost_const)
+        c->cvc_variant = value;
+        return PSM_OK;
     case 105:  // tuning: 1 = no packed remainder strips (one warp per slice for the last W % 112 columns, as in round 1)
         c->cvf_no_pack = value ? 1 : 0;
         return PSM_OK;
@@ -597,7 +600,14 @@ int psm_cost_const(psm_ctx* c)
     }
     {
         dim3 blk(128), grd((((c->W + 3) / 4) + 127) / 128, c->H, 2);
-        cvc_both_kernel<<<grd, blk, 0, c->stream>>>(P2);
+        // option 106 (tuning): 0 shipped = scalar window loads, 70 registers; 1 / 3 = one 128-bit window load per plane per four
+        // disparities without / with a register cap (109 / 96 registers).  Measured at C4: 0.497 / 0.501 / 0.533 ms -- the
+        // kernel is bound by its 2.1 GB of streaming stores, not by the window loads.
+        switch (c->cvc_variant) {
+        case 1: cvc_both_kernel<4, 1><<<grd, blk, 0, c->stream>>>(P2); break;
+        case 3: cvc_both_kernel<5, 1><<<grd, blk, 0, c->stream>>>(P2); break;
+        default: cvc_both_kernel<7, 0><<<grd, blk, 0, c->stream>>>(P2); break;
+        }
         PSM_LAUNCH_CHECK(c);
         if (!P2.v[0].fold_halo)  // narrow images: separate halo pass (general reflection)
             for (int v = 0; v < 2; ++v)

@@ -84,7 +84,9 @@ __global__ void ingest_kernel(const T* __restrict__ src, size_t step_bytes, int 
 // ------------------------------------------------------------------------------------------
 // K1 CVC.  One thread = 4 consecutive pixels of one row of ONE view; it walks the owned
 // disparities keeping the matched window of the other image in registers (one new scalar load
-// per plane per disparity) and writes one 128-bit store per slice.
+// per plane per disparity; GROUPED builds take one 128-bit load per plane per FOUR disparities when
+// the shard starts at a multiple of 4 -- same speed, more registers, kept for A/B) and writes one
+// 128-bit store per slice.
 //   left  volume (SIGN=-1): x >= d     ? cost4(L[x], R[x-d]) : border(L[x])   CVC.cpp:122-149
 //   right volume (SIGN=+1): x <  W - d ? cost4(R[x], L[x+d]) : border(R[x])   CVC.cpp:151-179
 // cost4 = CVC.cpp:18-27 (float), border = CVC.cpp:30-39 (double intermediates, BC_32F = 1.0).
@@ -114,21 +116,20 @@ __device__ __forceinline__ float cost_border(float l0, float l1, float l2, float
     return fadd(fmul(0.9f, clr), fmul(fsub(1.0f, 0.9f), grd));
 }
 
-template <int SIGN>
+template <int SIGN, int GROUPED>
 __device__ __forceinline__ void cvc_body(const CvcParams& P);
 
-// both volumes in ONE launch (blockIdx.z = view): twice the CTAs in flight and no tail between the two views
+// both volumes in ONE launch (blockIdx.z = view): twice the CTAs in flight and no tail between the two views.
+// MINB = resident CTAs per SM the register budget is cut for; GROUPED = 0 compiles only the scalar-load window (A/B).
 struct CvcParams2 { CvcParams v[2]; };
-__global__ void __launch_bounds__(128) cvc_both_kernel(const CvcParams2 P2)
+template <int MINB, int GROUPED>
+__global__ void __launch_bounds__(128, MINB) cvc_both_kernel(const CvcParams2 P2)
 {
-    if (blockIdx.z == 0) cvc_body<-1>(P2.v[0]);
-    else cvc_body<+1>(P2.v[1]);
+    if (blockIdx.z == 0) cvc_body<-1, GROUPED>(P2.v[0]);
+    else cvc_body<+1, GROUPED>(P2.v[1]);
 }
 
-template <int SIGN>
-__global__ void __launch_bounds__(128) cvc_kernel(CvcParams P) { cvc_body<SIGN>(P); }
-
-template <int SIGN>
+template <int SIGN, int GROUPED>
 __device__ __forceinline__ void cvc_body(const CvcParams& P)
 {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -152,14 +153,7 @@ __device__ __forceinline__ void cvc_body(const CvcParams& P)
     const float* o3 = P.other[3] + ro;
     auto clampx = [W](int x) { return x < 0 ? 0 : (x >= W ? W - 1 : x); };
 
-    // window w[c][j] = other[c][x4 + j + SIGN*d]
-    float w[4][4];
     int d = P.d_begin;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int xo = clampx(x4 + j + SIGN * d);
-        w[0][j] = __ldg(o0 + xo); w[1][j] = __ldg(o1 + xo); w[2][j] = __ldg(o2 + xo); w[3][j] = __ldg(o3 + xo);
-    }
     const size_t slice = (size_t)P.H * P.Wp;
     float* out = P.vol + ro + x4;
     // mirrored column halo (see pad_cols_kernel), written here for W >= 32: pixel x in [1,8] also goes to
@@ -177,15 +171,14 @@ __device__ __forceinline__ void cvc_body(const CvcParams& P)
         edge |= halo_off[j] != 0;
     }
     const bool full_group = x4 + 3 < W || !P.fold_halo;
-#pragma unroll 4
-    for (int dl = 0; dl < P.d_count; ++dl, ++d) {
+    auto emit = [&](int dl, int dd, const float (&m)[4][4]) {   // m[c][j]: matched pixel of plane c for pixel j at disparity dd
         float4 r;
         float* rp = reinterpret_cast<float*>(&r);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int x = x4 + j;
-            const bool interior = (SIGN < 0) ? (x >= d) : (x < W - d);
-            const float c = cost4(s[0][j], s[1][j], s[2][j], s[3][j], w[0][j], w[1][j], w[2][j], w[3][j]);
+            const bool interior = (SIGN < 0) ? (x >= dd) : (x < W - dd);
+            const float c = cost4(s[0][j], s[1][j], s[2][j], s[3][j], m[0][j], m[1][j], m[2][j], m[3][j]);
             rp[j] = (x < W) ? (interior ? c : bord[j]) : 0.f;
         }
         float* o = out + (size_t)dl * slice;
@@ -198,6 +191,65 @@ __device__ __forceinline__ void cvc_body(const CvcParams& P)
 #pragma unroll
             for (int j = 0; j < 4; ++j) if (halo_off[j] != 0) o[halo_off[j]] = rp[j];
         }
+    };
+
+    if (GROUPED && (P.d_begin & 3) == 0) {
+        // Aligned shard (every D/N split of the BASELINE configs): four disparities per block.  With d % 4 == 0 the matched
+        // positions x4 + j -/+ (d + k), k = 0..3, lie in two ALIGNED 4-column groups of the other view, and the next block
+        // needs exactly one new group per plane -- one 128-bit load per plane per four slices instead of four scalar loads.
+        // A group that lies wholly outside [0, W) is only ever matched by border pixels (whose cost is bord[j]), so its
+        // address is clamped to a valid group and its contents do not matter.
+        const int glast = (W - 1) & ~3;
+        auto group = [&](const float* base, int g) {
+            g = g < 0 ? 0 : (g > glast ? glast : g);
+            return __ldg(reinterpret_cast<const float4*>(base + g));
+        };
+        const float* ob[4] = {o0, o1, o2, o3};
+        int mb = x4 + SIGN * d;                       // first matched column of pixel 0 at this block's first disparity
+        float4 lo[4], hi[4];                          // columns [g, g+4) and [g+4, g+8) with g = mb - 4 (left) / mb (right)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            lo[c] = group(ob[c], SIGN < 0 ? mb - 4 : mb);
+            hi[c] = group(ob[c], SIGN < 0 ? mb : mb + 4);
+        }
+        for (int dl = 0; dl < P.d_count; dl += 4, d += 4) {
+            float4 nx[4];                             // the group the next block adds, loaded ahead of this block's arithmetic
+#pragma unroll
+            for (int c = 0; c < 4; ++c) nx[c] = group(ob[c], SIGN < 0 ? mb - 8 : mb + 8);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (dl + k < P.d_count) {
+                    float m[4][4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            // element of the 8-column window [lo | hi]: left j - k + 4 (1..7), right j + k (0..6)
+                            const int e = SIGN < 0 ? j - k + 4 : j + k;
+                            m[c][j] = e < 4 ? comp(lo[c], e) : comp(hi[c], e - 4);
+                        }
+                    emit(dl + k, d + k, m);
+                }
+            }
+            mb += 4 * SIGN;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (SIGN < 0) { hi[c] = lo[c]; lo[c] = nx[c]; }
+                else { lo[c] = hi[c]; hi[c] = nx[c]; }
+            }
+        }
+        return;
+    }
+    // unaligned shard: window w[c][j] = other[c][x4 + j + SIGN*d], one new scalar load per plane per disparity
+    float w[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int xo = clampx(x4 + j + SIGN * d);
+        w[0][j] = __ldg(o0 + xo); w[1][j] = __ldg(o1 + xo); w[2][j] = __ldg(o2 + xo); w[3][j] = __ldg(o3 + xo);
+    }
+#pragma unroll 4
+    for (int dl = 0; dl < P.d_count; ++dl, ++d) {
+        emit(dl, d, w);
         // slide the window by one disparity
         if (SIGN < 0) {
             const int xo = clampx(x4 - (d + 1));

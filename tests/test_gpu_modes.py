@@ -65,6 +65,26 @@ def test_guide_outside_the_integer_domain(oracle):
     assert_same(g["ld"], ref["lDis"], "lDisMap")
 
 
+# CVC builds (option 106): 0 = shipped (scalar window loads), 1 / 3 = one 128-bit window load per plane per four disparities
+# when the shard starts at a multiple of 4 (without / with a register cap; an unaligned shard falls back to the scalar
+# loop).  Raw volumes equal the oracle's for aligned / unaligned shards, depths that are not multiples of 4, widths that
+# are not multiples of 4 and disparities beyond the image width.
+@pytest.mark.parametrize("cvc_variant", [0, 1, 3])
+@pytest.mark.parametrize("W,H,D,d_begin,d_count", [(450, 37, 64, 0, 64), (451, 20, 21, 0, 21), (130, 24, 40, 8, 13),
+                                                   (130, 24, 40, 7, 9), (37, 16, 48, 0, 48), (1280, 9, 64, 32, 32),
+                                                   (253, 12, 256, 128, 128), (66, 10, 7, 4, 3)])
+def test_cvc_builds_raw_volumes(W, H, D, d_begin, d_count, cvc_variant, oracle):
+    rng = np.random.default_rng(W + 31 * D)
+    l = rng.random((H, W, 3), dtype=np.float32)
+    r = np.clip(np.roll(l, -5, axis=1) + rng.normal(0, 0.05, (H, W, 3)), 0, 1).astype(np.float32)
+    _, _, lraw, rraw = oracle.cost_const(l, r, D)
+    with DispEst(l, r, D, d_begin=d_begin, d_count=d_count) as de:
+        de.set_option(106, cvc_variant)
+        assert de.CostConst_GPU() == 0
+        assert_same(de.read_cost_volume(0), lraw[d_begin:d_begin + d_count], f"left raw volume, CVC build {cvc_variant}")
+        assert_same(de.read_cost_volume(1), rraw[d_begin:d_begin + d_count], f"right raw volume, CVC build {cvc_variant}")
+
+
 # Packed remainder strips (psm_cvf_stream.cuh): the W % 112 rightmost columns are filtered 4 slices per warp (remainder
 # <= 16 columns: 113, 128, 227, 240), 2 slices per warp (<= 48 columns: 129, 160, 260) or by a whole warp per slice
 # (161, 300: the round-1 decomposition, also what option 105 = 1 forces).  D = 5, 9, 13 leave slice groups of the last
