@@ -12,4 +12,6 @@ python bench.py --steps 10 --warmup 3 --workload C5 --no-cpu-baseline > gpurun_o
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference.json 2>> gpurun_out/bench_err.log
 python tools/pp_time.py C4 > gpurun_out/r2_pp_time.txt 2>&1
 python tools/fgf_time.py > gpurun_out/r2_fgf_time.txt 2>&1
-tail -3 gpurun_out/bench_err.log; cut -c1-300 gpurun_out/r2_bench_c4_exact.json; cat gpurun_out/r2_pp_time.txt gpurun_out/r2_fgf_time.txt; du -sh gpurun_out
+python tools/write_peak.py > gpurun_out/r2_write_peak.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_final.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_final.log; tail -3 gpurun_out/pytest_final.log
+tail -3 gpurun_out/bench_err.log; cut -c1-300 gpurun_out/r2_bench_c4_exact.json; cat gpurun_out/r2_pp_time.txt gpurun_out/r2_fgf_time.txt gpurun_out/r2_write_peak.txt; du -sh gpurun_out
