@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--extra-smem", type=int, default=0)
     ap.add_argument("--cta-threads", type=int, default=0)
     ap.add_argument("--remap", type=int, default=0)
+    ap.add_argument("--cvc-chunk", type=int, default=0, help="slices per CTA of the CVC kernel (tuning A/B, option 108)")
+    ap.add_argument("--guide-rows", type=int, default=0, help="rows per warp of the guide precompute (tuning A/B, option 107)")
     ap.add_argument("--cvc-variant", type=int, default=0, help="CVC kernel build (tuning A/B, option 106)")
     ap.add_argument("--no-pack", type=int, default=0, help="1: one warp per slice for the last W %% 112 columns (tuning A/B)")
     ap.add_argument("--upload", default="banded", choices=["banded", "replicated"],
@@ -254,6 +256,8 @@ def main():
     de.set_option(104, args.remap)
     de.set_option(105, args.no_pack)
     de.set_option(106, args.cvc_variant)
+    de.set_option(107, args.guide_rows)
+    de.set_option(108, args.cvc_chunk)
     stream = torch.cuda.Stream()  # a real (non-default) stream shared by the context and torch's collectives
     torch.cuda.set_stream(stream)
     capi.check(L.psm_set_stream(de.handle, C.c_void_p(stream.cuda_stream)), de.handle)

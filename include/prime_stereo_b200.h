@@ -70,12 +70,15 @@ enum {
     PSM_OPT_P2P_SYNC = 4   /* fused multi-GPU exchange: 1 (default) = the kernels synchronise across ranks by
                               device-side flags in the exchange blocks (no library collective, no host barrier);
                               0 = the caller separates select / reduce / fetch by its own cross-rank barriers */
-    /* keys 100..104 are kernel tuning knobs used by bench.py experiments (variant, rows per segment, extra
-       shared memory, threads per CTA, block remap); they never change results */
+    /* keys 100..106 are kernel tuning knobs used by bench.py experiments (variant, rows per segment, extra
+       shared memory, threads per CTA, block remap, packed remainder strips off, CVC build); they never
+       change results */
 };
 enum {
     PSM_CVF_EXACT = 0, /* streaming fused kernel, every box sum accumulated in fp64: bit-exact q */
-    PSM_CVF_MIXED = 1, /* reserved (fp32 second stage); not built: psm_set_option returns PSM_EINVAL */
+    PSM_CVF_MIXED = 1, /* the tolerance mode north_star allows for fp32: first box stage fp64 (a, b bit-exact), second
+                          box stage fp32 with a fixed summation tree: q within ~3e-6 of EXACT, deterministic
+                          (tests/mixed_model.py restates it on the CPU); same maps as EXACT on every tested frame */
     PSM_CVF_NAIVE = 2  /* unfused two-pass direct 64-tap fp64 kernels: slow device-side cross-check */
 };
 

@@ -69,7 +69,7 @@ struct psm_ctx {
     size_t ab_slices = 0;
     cudaEvent_t ev0[kNumStages] = {}, ev1[kNumStages] = {};
     bool ev_valid[kNumStages] = {};
-    int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0, cvf_target_rows = 0, cvf_extra_smem = 0, cvf_threads = 0, cvf_remap = 0, cvf_no_pack = 0, cvc_variant = 0;
+    int cvf_mode = PSM_CVF_EXACT, gray_mode = 0, timing = 1, cvf_variant = 0, cvf_target_rows = 0, cvf_extra_smem = 0, cvf_threads = 0, cvf_remap = 0, cvf_no_pack = 0, cvc_variant = 0, guide_seg_rows = 0, cvc_chunk = 0;
     bool have_images = false, guide_valid = false, have_cvc = false, filtered = false;
     uint64_t launches = 0;
     char err[512] = "";
@@ -192,7 +192,8 @@ int ensure_guide(psm_ctx* c)
     P.guide_flags = c->guide_flags;
     P.W = c->W; P.H = c->H; P.Wp = c->Wp;
     P.nstrips = (c->W + kGuideStripOut - 1) / kGuideStripOut;
-    P.nseg = (c->H + kGuideSegRows - 1) / kGuideSegRows;
+    P.seg_rows = c->guide_seg_rows > 0 ? c->guide_seg_rows : kGuideSegRows;   // option 107 (tuning)
+    P.nseg = (c->H + P.seg_rows - 1) / P.seg_rows;
     const int tasks = 2 * P.nstrips * P.nseg;  // one warp each
     guide_kernel<<<(tasks + 3) / 4, 128, 0, c->stream>>>(P);
     PSM_LAUNCH_CHECK(c);
@@ -492,6 +493,15 @@ int psm_set_option(psm_ctx* c, int key, int value)
     case 100:  // streaming-kernel variant selector for tuning experiments
         c->cvf_variant = value;
         return PSM_OK;
+    case 108:  // tuning: slices per CTA of the CVC kernel (0 = all)
+        if (value < 0) return fail(c, PSM_EINVAL, "bad CVC chunk");
+        c->cvc_chunk = value;
+        return PSM_OK;
+    case 107:  // tuning: rows per warp of the guide precompute (0 = default)
+        if (value < 0 || value > 4096) return fail(c, PSM_EINVAL, "bad guide segment rows");
+        c->guide_seg_rows = value;
+        c->guide_valid = false;
+        return PSM_OK;
     case 106:  // tuning: CVC kernel build (see psm_cost_const)
         c->cvc_variant = value;
         return PSM_OK;
@@ -599,12 +609,15 @@ int psm_cost_const(psm_ctx* c)
         P.fold_halo = c->W >= 32 ? 1 : 0;
     }
     {
-        dim3 blk(128), grd((((c->W + 3) / 4) + 127) / 128, c->H, 2);
-        // option 106 (tuning): 0 shipped = scalar window loads, 70 registers; 1 / 3 = one 128-bit window load per plane per four
-        // disparities without / with a register cap (109 / 96 registers).  Measured at C4: 0.497 / 0.501 / 0.533 ms -- the
-        // kernel is bound by its 2.1 GB of streaming stores, not by the window loads.
+        // option 108 (tuning): slices per CTA (0 = all owned slices in one CTA, the shipped decomposition)
+        P2.chunk = (c->cvc_chunk > 0 && c->cvc_chunk < c->d_count) ? c->cvc_chunk : 0;
+        const int nchunks = P2.chunk ? (c->d_count + P2.chunk - 1) / P2.chunk : 1;
+        dim3 blk(128), grd((((c->W + 3) / 4) + 127) / 128, c->H, 2 * nchunks);
+        // option 106 (tuning): 0 shipped = interior fast path + scalar window loads; 2 = no fast path (the round-1 loop);
+        // 1 / 3 = fast path + grouped 128-bit window loads for the border warps without / with a register cap
         switch (c->cvc_variant) {
         case 1: cvc_both_kernel<4, 1><<<grd, blk, 0, c->stream>>>(P2); break;
+        case 2: cvc_both_kernel<7, 2><<<grd, blk, 0, c->stream>>>(P2); break;
         case 3: cvc_both_kernel<5, 1><<<grd, blk, 0, c->stream>>>(P2); break;
         default: cvc_both_kernel<7, 0><<<grd, blk, 0, c->stream>>>(P2); break;
         }

@@ -120,13 +120,25 @@ template <int SIGN, int GROUPED>
 __device__ __forceinline__ void cvc_body(const CvcParams& P);
 
 // both volumes in ONE launch (blockIdx.z = view): twice the CTAs in flight and no tail between the two views.
-// MINB = resident CTAs per SM the register budget is cut for; GROUPED = 0 compiles only the scalar-load window (A/B).
-struct CvcParams2 { CvcParams v[2]; };
+// MINB = resident CTAs per SM the register budget is cut for; GROUPED: 0 = shipped (interior fast path + scalar-load window for the
+// border warps), 1 = border / all warps use grouped 128-bit window loads when the shard is aligned (A/B), 2 = no fast path (round-1 loop).
+// blockIdx.z = chunk * 2 + view: with chunk > 0 (P2.chunk slices per CTA instead of all owned slices) the grid walks the volume
+// chunk by chunk -- z is the slowest block index -- so that at any moment the GPU writes a few neighbouring slices instead of one
+// 2 KB run in each of 128 slices 8 MB apart (DRAM page locality of the 2.1 GB store stream).
+struct CvcParams2 { CvcParams v[2]; int chunk; };
 template <int MINB, int GROUPED>
 __global__ void __launch_bounds__(128, MINB) cvc_both_kernel(const CvcParams2 P2)
 {
-    if (blockIdx.z == 0) cvc_body<-1, GROUPED>(P2.v[0]);
-    else cvc_body<+1, GROUPED>(P2.v[1]);
+    const int view = blockIdx.z & 1, chunk = blockIdx.z >> 1;
+    CvcParams P = P2.v[view];
+    if (P2.chunk > 0) {
+        const int first = chunk * P2.chunk;
+        P.vol += (size_t)first * P.H * P.Wp;
+        P.d_begin += first;
+        P.d_count = min(P2.chunk, P.d_count - first);
+    }
+    if (view == 0) cvc_body<-1, GROUPED>(P);
+    else cvc_body<+1, GROUPED>(P);
 }
 
 template <int SIGN, int GROUPED>
@@ -193,7 +205,40 @@ __device__ __forceinline__ void cvc_body(const CvcParams& P)
         }
     };
 
-    if (GROUPED && (P.d_begin & 3) == 0) {
+    // Interior fast path: a warp whose 128 pixels are matched inside the image for EVERY owned disparity (left volume: x >= the
+    // largest d; right volume: x + largest d < W), away from the mirrored-halo columns and the ragged last group -- 13 of the 15
+    // warps of a 1920-pixel row at D = 128 -- runs the same arithmetic without the per-pixel interior / x < W selects, the address
+    // clamps and the halo branches: ~50 instead of ~98 instructions per 128-bit store.  (The one load past the matched range in
+    // the last iteration lands in the row's mirrored halo and is never used.)
+    if (GROUPED != 2) {
+        const int dmax = P.d_begin + P.d_count - 1;
+        const bool all_in = (SIGN < 0) ? (x4 >= dmax) : (x4 + 3 < W - dmax);
+        if (__all_sync(0xffffffffu, all_in && !edge && x4 + 3 < W)) {
+            const float* q[4] = {o0 + x4, o1 + x4, o2 + x4, o3 + x4};
+            float w[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w[c][j] = __ldg(q[c] + j + SIGN * d);
+            float* o = out;
+#pragma unroll 4
+            for (int dl = 0; dl < P.d_count; ++dl, ++d, o += slice) {
+                float4 r;
+                r.x = cost4(s[0][0], s[1][0], s[2][0], s[3][0], w[0][0], w[1][0], w[2][0], w[3][0]);
+                r.y = cost4(s[0][1], s[1][1], s[2][1], s[3][1], w[0][1], w[1][1], w[2][1], w[3][1]);
+                r.z = cost4(s[0][2], s[1][2], s[2][2], s[3][2], w[0][2], w[1][2], w[2][2], w[3][2]);
+                r.w = cost4(s[0][3], s[1][3], s[2][3], s[3][3], w[0][3], w[1][3], w[2][3], w[3][3]);
+                __stcs(reinterpret_cast<float4*>(o), r);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (SIGN < 0) { w[c][3] = w[c][2]; w[c][2] = w[c][1]; w[c][1] = w[c][0]; w[c][0] = __ldg(q[c] - (d + 1)); }
+                    else { w[c][0] = w[c][1]; w[c][1] = w[c][2]; w[c][2] = w[c][3]; w[c][3] = __ldg(q[c] + 3 + (d + 1)); }
+                }
+            }
+            return;
+        }
+    }
+    if (GROUPED == 1 && (P.d_begin & 3) == 0) {
         // Aligned shard (every D/N split of the BASELINE configs): four disparities per block.  With d % 4 == 0 the matched
         // positions x4 + j -/+ (d + k), k = 0..3, lie in two ALIGNED 4-column groups of the other view, and the next block
         // needs exactly one new group per plane -- one 128-bit load per plane per four slices instead of four scalar loads.
@@ -344,7 +389,7 @@ __device__ __forceinline__ void hsum8(const double c[4], double h[4])
     h[3] = (S1 + Tn) + Q3;
 }
 
-// K2: warp = strip of 128 input columns (120 output columns) x kGuideSegRows rows of one view;
+// K2: warp = strip of 128 input columns (120 output columns) x seg_rows rows of one view;
 // lane = 4 columns.  fp64 running column sums of the nine planes (newest row added, oldest row
 // removed, both re-read from the I planes whose column halo is mirrored), 8-wide row sums by
 // hsum8, then guide_solve per pixel; every plane is written with 128-bit stores.
@@ -354,7 +399,7 @@ constexpr int kGuideStripOut = 120;
 struct GuideParams {
     float* guide[2];
     int* guide_flags;   // [2]: bit 1 raised when a mean / adjugate / 1/det value is not finite
-    int W, H, Wp, nstrips, nseg;
+    int W, H, Wp, nstrips, nseg, seg_rows;
 };
 
 __global__ void __launch_bounds__(128) guide_kernel(const GuideParams P)
@@ -372,8 +417,8 @@ __global__ void __launch_bounds__(128) guide_kernel(const GuideParams P)
     const int co = cin + 4;
     const bool in_ok = cin <= W + 4;       // beyond: nothing this lane feeds is ever stored (and the halo ends at W+7)
     const bool out_ok = lane <= 29 && co < W;
-    const int y0 = seg * kGuideSegRows;
-    const int y1 = min(H, y0 + kGuideSegRows);
+    const int y0 = seg * P.seg_rows;
+    const int y1 = min(H, y0 + P.seg_rows);
 
     double V[9][4];
 #pragma unroll
@@ -381,11 +426,8 @@ __global__ void __launch_bounds__(128) guide_kernel(const GuideParams P)
 #pragma unroll
         for (int j = 0; j < 4; ++j) V[k][j] = 0.0;
 
-    // f32 -> f64 as in the streaming filter (psm_cvf_stream.cuh): image values and their products are non-negative, so
-    // bits(u) * 2^29 is the double f * 2^-896 (one IMAD.WIDE.U32 instead of an F2F); the sums stay in that scaled domain
-    // and the scale is folded into the final multiply.  A guide flagged by ingest_kernel (negative / non-finite image
-    // values) converts with F2F and rescales instead.
-    const bool fastw = (P.guide_flags[view] & 1) == 0;   // bit 0 is final before this launch (bit 1 is raised below)
+    // (widening I and I*I' with the integer trick of the streaming filter was measured here and is 15 % SLOWER, 119 vs 104 us:
+    // this kernel has XU slack and the IMAD.WIDEs land on the FMA pipe next to its multiplies -- plain conversions stay)
     auto feed = [&](int r, const bool add) {
         const size_t ro = (size_t)reflect101(r, H) * Wp + cin;
         float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4, c4 = a4;
@@ -399,10 +441,7 @@ __global__ void __launch_bounds__(128) guide_kernel(const GuideParams P)
             const float a = comp(a4, j), b = comp(b4, j), c = comp(c4, j);
             const float t[9] = {a, b, c, fmul(a, a), fmul(a, b), fmul(a, c), fmul(b, b), fmul(b, c), fmul(c, c)};  // CVF.cpp:62
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const double w = fastw ? widen_nn(t[k]) : widen_any(t[k]);
-                V[k][j] = add ? __dadd_rn(V[k][j], w) : __dsub_rn(V[k][j], w);
-            }
+            for (int k = 0; k < 9; ++k) V[k][j] = add ? __dadd_rn(V[k][j], (double)t[k]) : __dsub_rn(V[k][j], (double)t[k]);
         }
     };
 
@@ -415,7 +454,7 @@ __global__ void __launch_bounds__(128) guide_kernel(const GuideParams P)
             double h[4];
             hsum8(V[k], h);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) m[k][j] = (float)__dmul_rn(h[j], kMeanScaled);
+            for (int j = 0; j < 4; ++j) m[k][j] = (float)__dmul_rn(h[j], kMeanPlain);
         }
         feed(y - kBoxAnchor, false);
         float o[16][4];  // planes kGuideMean .. kGuidePlanes-1

@@ -65,11 +65,12 @@ def test_guide_outside_the_integer_domain(oracle):
     assert_same(g["ld"], ref["lDis"], "lDisMap")
 
 
-# CVC builds (option 106): 0 = shipped (scalar window loads), 1 / 3 = one 128-bit window load per plane per four disparities
-# when the shard starts at a multiple of 4 (without / with a register cap; an unaligned shard falls back to the scalar
-# loop).  Raw volumes equal the oracle's for aligned / unaligned shards, depths that are not multiples of 4, widths that
-# are not multiples of 4 and disparities beyond the image width.
-@pytest.mark.parametrize("cvc_variant", [0, 1, 3])
+# CVC builds (option 106): 0 = shipped (interior fast path for the warps that are matched inside the image at every owned
+# disparity + scalar window loads elsewhere), 2 = no fast path (the round-1 loop), 1 / 3 = fast path + one 128-bit window load
+# per plane per four disparities for the other warps when the shard starts at a multiple of 4.  Raw volumes equal the oracle's
+# for aligned / unaligned shards, depths that are not multiples of 4, widths that are not multiples of 4 (partial warps), wide
+# rows where most warps take the fast path, and disparities beyond the image width (no warp does).
+@pytest.mark.parametrize("cvc_variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("W,H,D,d_begin,d_count", [(450, 37, 64, 0, 64), (451, 20, 21, 0, 21), (130, 24, 40, 8, 13),
                                                    (130, 24, 40, 7, 9), (37, 16, 48, 0, 48), (1280, 9, 64, 32, 32),
                                                    (253, 12, 256, 128, 128), (66, 10, 7, 4, 3)])
@@ -105,6 +106,20 @@ def test_packed_remainder_strips(W, H, D, no_pack, oracle):
     m = run_gpu(l, r, D, mode=capi.PSM_CVF_MIXED, options=[(105, no_pack)])
     for img, raw, key in ((l, g["lraw"], "lf"), (r, g["rraw"], "rf")):
         assert_same(m[key], MM.cost_filter_mixed(oracle, img, raw), f"MIXED {key} vs CPU model, no_pack={no_pack}")
+
+
+@pytest.mark.parametrize("rows", [8, 12, 16, 24, 100])
+def test_guide_precompute_segment_rows(rows, scenes, oracle):
+    """Option 107: rows per warp of the guide precompute (each segment restarts its fp64 column sums)."""
+    _, _, l, r = scenes["Teddy"]
+    _, mean, var = oracle.cvf_preprocess(l)
+    with DispEst(l, r, 8) as de:
+        de.set_option(107, rows)
+        de.CostConst_GPU()
+        for c in range(3):
+            assert_same(de.read_guide_plane(0, 3 + c), mean[c], f"mean_I {c}, {rows} rows per warp")
+        for k in range(6):
+            assert_same(de.read_guide_plane(0, 6 + k), var[k], f"var_I {k}, {rows} rows per warp")
 
 
 @pytest.mark.parametrize("log2_scale", [0, 40, 70])

@@ -106,6 +106,23 @@ def main():
     other = os.path.join(OUT, "r2_other_kernels_raw.csv")
     if os.path.exists(other):
         json.dump([summarize(r) for r in raw_rows(other)], open(os.path.join(PROF, "r2_other_kernels_summary.json"), "w"), indent=1)
+    # the other kernels of the frame: CVC builds (with their source pages) and the small per-frame kernels
+    for tag in ("cvc_v0", "cvc_v1", "cvc_fast"):
+        raw = os.path.join(OUT, f"r2_{tag}_raw.csv")
+        if not os.path.exists(raw):
+            continue
+        s = summarize(raw_rows(raw)[-1])
+        src = os.path.join(OUT, f"r2_{tag}_source.csv.gz")
+        if os.path.exists(src):
+            total, mix, stalls = source_mix(src)
+            tot_s = sum(stalls.values()) or 1
+            s["executed_warp_instructions"] = total
+            s["instruction_mix_top"] = {k: v for k, v in mix.most_common(14)}
+            s["warp_state_samples_pct"] = {k[6:]: round(100.0 * v / tot_s, 1) for k, v in stalls.most_common(10)}
+        json.dump(s, open(os.path.join(PROF, f"r2_{tag}_summary.json"), "w"), indent=1)
+    small = os.path.join(OUT, "r2_small_kernels_raw.csv")
+    if os.path.exists(small):
+        json.dump([summarize(r) for r in raw_rows(small)], open(os.path.join(PROF, "r2_small_kernels_summary.json"), "w"), indent=1)
     print(json.dumps(facts, indent=1)[:1500])
 
 
