@@ -86,6 +86,22 @@ def test_cvc_builds_raw_volumes(W, H, D, d_begin, d_count, cvc_variant, oracle):
         assert_same(de.read_cost_volume(1), rraw[d_begin:d_begin + d_count], f"right raw volume, CVC build {cvc_variant}")
 
 
+@pytest.mark.parametrize("chunk", [5, 8, 16, 100])
+def test_cvc_slice_chunks(chunk, oracle):
+    """Option 108: slices per CTA of the CVC kernel (the grid then walks the volume chunk by chunk); incl. a ragged last chunk."""
+    rng = np.random.default_rng(chunk)
+    W, H, D = 300, 21, 37
+    l = rng.random((H, W, 3), dtype=np.float32)
+    r = np.clip(np.roll(l, -4, axis=1) + rng.normal(0, 0.05, (H, W, 3)), 0, 1).astype(np.float32)
+    _, _, lraw, rraw = oracle.cost_const(l, r, D)
+    for d_begin, d_count in ((0, D), (8, 20)):
+        with DispEst(l, r, D, d_begin=d_begin, d_count=d_count) as de:
+            de.set_option(108, chunk)
+            assert de.CostConst_GPU() == 0
+            assert_same(de.read_cost_volume(0), lraw[d_begin:d_begin + d_count], f"left raw volume, chunk {chunk}")
+            assert_same(de.read_cost_volume(1), rraw[d_begin:d_begin + d_count], f"right raw volume, chunk {chunk}")
+
+
 # Packed remainder strips (psm_cvf_stream.cuh): the W % 112 rightmost columns are filtered 4 slices per warp (remainder
 # <= 16 columns: 113, 128, 227, 240), 2 slices per warp (<= 48 columns: 129, 160, 260) or by a whole warp per slice
 # (161, 300: the round-1 decomposition, also what option 105 = 1 forces).  D = 5, 9, 13 leave slice groups of the last
