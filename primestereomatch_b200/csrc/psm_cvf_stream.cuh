@@ -40,8 +40,8 @@
 //   stage 1: S1[4 boxes][4 cols] fp64 running column sums of p, I0*p, I1*p, I2*p;
 //            row sums = per-lane prefix/suffix sums + 4 fp64 shuffles per box (lane+1 total, lane+2 prefixes)
 //   a,b    : CVF.cpp:92-155 with the d-independent adjugate / 1/det precomputed per pixel (K2)
-//   ring   : thread-private 8-slot history in shared memory (512 B per thread), the only on-chip
-//            history: stage-1 "oldest rows" are re-read from the raw volume (L1/L2).
+//   ring   : thread-private 8-slot history (512 B per thread) in TENSOR MEMORY (below; shared memory in the TM = 0
+//            builds), the only on-chip history: stage-1 "oldest rows" are re-read from the raw volume (L1/L2).
 //            EXACT: slots hold a,b rows;  MIXED: slots hold PAIR rows  pair(t) = ab(t-1) + ab(t)
 //   stage 2 EXACT: S2[4 planes][4 cols] fp64 running column sums of a0,a1,a2,b (newest from
 //            registers, oldest from the ring); row sums as in stage 1
@@ -51,8 +51,8 @@
 //            groups (strip origins are multiples of 4, so the tree depends on x only)
 //   q = box(b) + sum_c box(a_c) * I_c   (CVF.cpp:157-163)
 //
-// Column bookkeeping of strip s (X0 = first output column, 112*s; the last strip is shifted left
-// to end at the image edge), lane l:
+// Column bookkeeping of strip s (X0 = first output column, 112*s; without the packed remainder the
+// last strip is shifted left to end at the image edge), lane l (packed remainder: lane within its group):
 //   input  columns X0-8+4l .. +3   (p, I)                  halo columns come from the mirrored halo
 //   a,b    columns X0-4+4l .. +3   (valid for l <= 29)     of the padded layout (psm_kernels.cuh)
 //   output columns X0  +4l .. +3   (valid for l <= 27)
@@ -78,7 +78,7 @@ namespace psm {
 
 constexpr int kStripOut = 112;  // output columns per warp
 constexpr int kStripIn = 128;   // input columns per warp
-constexpr int kCvfThreads = 96;       // default CTA size: 3 slice-warps, 48 KB ring, 4 CTAs/SM
+constexpr int kCvfThreads = 96;       // CTA size when the slice count is not a multiple of 4: 3 slice-warps, 4 CTAs/SM (else 128 x 3)
 constexpr int kCvfMaxThreads = 512;   // 16 warps: every ring of an SM's tensor memory in one CTA
 
 // stage-2 modes (template parameter S2M)
