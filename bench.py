@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--extra-smem", type=int, default=0)
     ap.add_argument("--cta-threads", type=int, default=0)
     ap.add_argument("--remap", type=int, default=0)
+    ap.add_argument("--emulate-shards", type=int, default=1,
+                    help="tuning: one GPU runs the per-rank share (D/N slices, no exchange) of an N-GPU run; not a benchmark line")
     ap.add_argument("--cvc-chunk", type=int, default=0, help="slices per CTA of the CVC kernel (tuning A/B, option 108)")
     ap.add_argument("--guide-rows", type=int, default=0, help="rows per warp of the guide precompute (tuning A/B, option 107)")
     ap.add_argument("--cvc-variant", type=int, default=0, help="CVC kernel build (tuning A/B, option 106)")
@@ -247,6 +249,10 @@ def main():
     torch.cuda.synchronize()
 
     d_begin, d_count = shard_range(D, world, rank)
+    if args.emulate_shards > 1:
+        assert world == 1
+        d_begin, d_count = shard_range(D, args.emulate_shards, 0)
+        args.no_parity = True
     de = DispEst(l, r, D, 8, True, device=local_rank, d_begin=d_begin, d_count=d_count)
     de.set_option(capi.PSM_OPT_CVF_MODE, args.cvf_mode)
     de.set_option(capi.PSM_OPT_VARIANT, args.variant)
@@ -271,6 +277,7 @@ def main():
         gathered = torch.empty((2, world, npix), dtype=torch.int64, device="cuda")
     elif world > 1:
         p2p = P2PExchange(de, world, rank, device_sync=(args.exchange == "p2p"))
+    emu_keys = torch.empty((2, npix), dtype=torch.int64, device="cuda") if args.emulate_shards > 1 else None
     step_bytes = W * 3 * 4
     banded = BandedUpload(de, world, rank) if (world > 1 and args.upload == "banded") else None
 
@@ -278,7 +285,9 @@ def main():
         """stages after the images are set: CVC, CVF, WTA (+ exchange), maps to host when e2e"""
         capi.check(L.psm_cost_const(de.handle), de.handle)
         capi.check(L.psm_cost_filter(de.handle), de.handle)
-        if world == 1:
+        if args.emulate_shards > 1:   # tuning: the rank's local WTA, no exchange
+            capi.check(L.psm_disp_select_keys(de.handle, emu_keys[0].data_ptr(), emu_keys[1].data_ptr()), de.handle)
+        elif world == 1:
             if e2e:  # D2H enqueued, not synchronised: the host maps are read after the timed region's final sync
                 capi.check(L.psm_disp_select_async(de.handle, lmap.data_ptr(), W, rmap.data_ptr(), W), de.handle)
             else:
@@ -362,6 +371,13 @@ def main():
     kms = kernel_times(args.steps)
     clocks = sampler.stop() if rank == 0 else None
     stage = {n: de.stage_ms(i) for i, n in enumerate(["ingest", "cvc", "cvf", "wta", "cvf_kernel"])}
+    if args.emulate_shards > 1:
+        print(json.dumps({"NOTE": "tuning run (one GPU runs the share of one rank of an N-GPU run, no exchange); not a benchmark line",
+                          "workload": WORKLOAD, "emulated_share_of": args.emulate_shards, "slices": d_count,
+                          "cvf_mode": MODES[args.cvf_mode], "ms_per_step": total_ms / args.steps,
+                          "cvf_kernel_ms": float(np.mean(kms)), "stage_ms_last_step": stage}), flush=True)
+        de.close()
+        return 0
     e2e_ms = timed(True, args.steps)
     e2e_u8_ms = timed("u8", args.steps)
 
@@ -425,6 +441,7 @@ def main():
             "config": {"workload": WORKLOAD,
                        "parallelism": (f"disparity-sharded x{world}, exchange={args.exchange}") if world > 1 else "single GPU",
                        "cvf_mode": mode, "variant": args.variant,
+                       **({"emulated_share_of": args.emulate_shards, "NOTE": "tuning run, not a benchmark line"} if args.emulate_shards > 1 else {}),
                        "l2": f"inputs larger than L2: each step streams {4 * V * 4 / 1e9:.2f} GB of volumes (raw+filtered, 2 views) per GPU"
                              + ("" if 4 * V * 4 > 252e6 else "; NOTE: smaller than 2 x L2, L2 reuse between steps is possible"),
                        "stage_ms_last_step": stage},

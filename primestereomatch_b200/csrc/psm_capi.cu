@@ -271,7 +271,10 @@ int launch_cvf_stream(psm_ctx* c)
             // the last wave rarely runs full length: count it in proportion to its fill, but never below half a wave
             const long rem = ctas - (waves - 1) * slots;
             const double last = rem >= slots ? 1.0 : (0.5 + 0.5 * (double)rem / (double)slots);
-            const long cost = (long)(((double)(waves - 1) + last) * (rows + 11) * 16);
+            // + half a CTA duration: CTAs do not finish in lock-step, and the shorter they are the shorter the ragged end of the
+            // kernel.  Fitted on measurements (profiles/r2_segrows_ab2.txt, r2_segrows_shards_ab.txt): C4 -> 4 segments, C3 -> 6,
+            // 16 slices of C4 (one of 8 ranks) -> 9, 32 slices of C5 -> 8, each the fastest or within 1 % of it.
+            const long cost = (long)(((double)(waves - 1) + last + 0.5) * (rows + 11) * 16);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_ns = ns; best_rows = rows; }
         }
     }
