@@ -82,6 +82,14 @@ enum {
     PSM_CVF_NAIVE = 2  /* unfused two-pass direct 64-tap fp64 kernels: slow device-side cross-check */
 };
 
+/* Diagnostic, needs no device: the work decomposition the streaming guided-filter kernel would use for a W x H x d_count
+ * problem on a GPU with sm_count SMs (no reference counterpart; the reference's unit of parallel work is the slice,
+ * src/DispEst.cpp:235-268).  out[0..9] = threads per CTA, full 112-column strips, slice groups, row segments, rows per
+ * segment, lanes per slice of the packed remainder (0 = none), first output-aligned column of the packed remainder,
+ * packed slice groups, first packed CTA, grid size.  The CPU tests check its invariants (every column and row of every
+ * slice is produced exactly once). */
+int psm_cvf_plan(int width, int height, int d_count, int sm_count, int no_pack, int* out, int n);
+
 /* Number of usable CUDA devices (0 if none / no driver): gates the `m` toggle. */
 int psm_device_count(void);
 

@@ -19,7 +19,7 @@ SYMBOLS = [
     "psm_post_process", "psm_post_process_device", "psm_cost_filter_fgf", "psm_disp_select_keys", "psm_disp_reduce_keys", "psm_p2p_create_buffer", "psm_ipc_export", "psm_ipc_import",
     "psm_p2p_set_peers", "psm_disp_select_keys_p2p", "psm_disp_reduce_p2p", "psm_disp_fetch_p2p", "psm_read_cost_slice", "psm_write_cost_slice",
     "psm_read_guide_plane", "psm_read_ab_slice", "psm_device_ptr", "psm_stage_ms",
-    "psm_launch_count", "psm_sync", "psm_last_error", "psm_build_info",
+    "psm_launch_count", "psm_sync", "psm_last_error", "psm_build_info", "psm_cvf_plan",
 ]
 
 PSM_OK, PSM_EINVAL, PSM_ECUDA, PSM_ESTATE, PSM_ENOMEM = 0, 1, 2, 3, 4
@@ -48,6 +48,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     vp, sz, i, u8p, fp = C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p
     L.psm_device_count.argtypes = []
+    L.psm_cvf_plan.argtypes = [i, i, i, i, i, C.POINTER(C.c_int), i]
     L.psm_create.argtypes = [C.POINTER(vp), i, i, i, i]
     L.psm_create_sharded.argtypes = [C.POINTER(vp), i, i, i, i, i, i]
     L.psm_destroy.argtypes = [vp]
@@ -99,3 +100,15 @@ def check(rc, ctx=None):
     if rc != 0:
         text = lib().psm_last_error(ctx)
         raise PsmError(rc, text.decode() if text else "?")
+
+
+PLAN_FIELDS = ("threads", "nstrips", "ndgroups", "nseg", "seg_rows", "pack_gl", "pack_x0", "pack_ndg", "pack_first", "grid")
+
+
+def cvf_plan(width, height, d_count, sm_count=148, no_pack=False):
+    """psm_cvf_plan as a dict (needs no device)."""
+    out = (C.c_int * 10)()
+    rc = lib().psm_cvf_plan(width, height, d_count, sm_count, 1 if no_pack else 0, out, 10)
+    if rc != PSM_OK:
+        raise PsmError(rc, "psm_cvf_plan: bad arguments")
+    return dict(zip(PLAN_FIELDS, list(out)))

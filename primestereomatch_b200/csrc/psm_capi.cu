@@ -227,50 +227,48 @@ void plan_segments(int H, int target_rows, int* nseg, int* seg_rows)
     *seg_rows = (H + 7) & ~7;
 }
 
-int launch_cvf_stream(psm_ctx* c)
+// The streaming kernel's work decomposition as a pure host function (no CUDA calls) so that the host logic can be
+// tested without a GPU (psm_cvf_plan, tests/test_cvf_plan.py).
+struct CvfPlan {
+    int nthreads, nstrips, ndgroups, nseg, seg_rows;
+    int pack_gl, pack_x0, pack_ndg, pack_first;
+    unsigned grid;
+};
+
+CvfPlan plan_cvf(int W, int H, int d_count, int nsm, int threads_override, int target_rows, bool allow_pack)
 {
-    CvfParams P;
-    for (int v = 0; v < 2; ++v) { P.vol_in[v] = c->vol[v]; P.vol_out[v] = c->vol_alt[v]; P.guide[v] = c->guide[v]; }
-    P.W = c->W; P.H = c->H; P.Wp = c->Wp; P.Dloc = c->d_count;
-    P.nstrips = (c->W + kStripOut - 1) / kStripOut;
-    // packed remainder strips (psm_cvf_stream.cuh): the columns past the last full strip, 4 or 2 slices per warp.  Needs the
-    // tensor-memory ring and no CTA-level staging (variants 1, 2 and 9 keep the plain decomposition); option 105 = 1 disables.
-    P.pack_gl = 0; P.pack_first = 0; P.pack_ndg = 0; P.pack_x0 = 0;
-    {
-        const bool plain_variant = c->cvf_variant == 9 || c->cvf_variant == 2 || (c->cvf_mode != PSM_CVF_MIXED && c->cvf_variant == 1);
-        const int nfull = c->W / kStripOut, rem = c->W - nfull * kStripOut;
-        if (!c->cvf_no_pack && !plain_variant && !c->cvf_remap && nfull >= 1 && rem > 0) {
-            for (int gl = 8; gl <= 16; gl *= 2) {
-                const int x0 = (c->W - 4 * (gl - 4) + 3) & ~3;
-                if (x0 <= nfull * kStripOut) { P.pack_gl = gl; P.pack_x0 = x0; P.nstrips = nfull; break; }
-            }
+    CvfPlan q{};
+    q.nstrips = (W + kStripOut - 1) / kStripOut;
+    // packed remainder strips (psm_cvf_stream.cuh): the columns past the last full strip, 4 or 2 slices per warp
+    const int nfull = W / kStripOut, rem = W - nfull * kStripOut;
+    if (allow_pack && nfull >= 1 && rem > 0) {
+        for (int gl = 8; gl <= 16; gl *= 2) {
+            const int x0 = (W - 4 * (gl - 4) + 3) & ~3;
+            if (x0 <= nfull * kStripOut) { q.pack_gl = gl; q.pack_x0 = x0; q.nstrips = nfull; break; }
         }
     }
     // slice-warps per CTA: 3 (4 CTAs per SM) or 4 (3 CTAs per SM) -- the same 12 warps per SM either way; take the one that
     // leaves no warp slot idle in the last slice group (16 slices per rank at 8 GPUs: 4 x 4 instead of 6 x 3 with two idle)
-    const int auto_threads = (c->d_count % 3 != 0 && c->d_count % 4 == 0) ? 128 : kCvfThreads;
-    const int nthreads = c->cvf_threads > 0 ? c->cvf_threads : auto_threads;
-    const int wpc = nthreads / 32;
-    P.ndgroups = (c->d_count + wpc - 1) / wpc;
-    if (P.pack_gl) P.pack_ndg = (c->d_count + wpc * (32 / P.pack_gl) - 1) / (wpc * (32 / P.pack_gl));
+    const int auto_threads = (d_count % 3 != 0 && d_count % 4 == 0) ? 128 : kCvfThreads;
+    q.nthreads = threads_override > 0 ? threads_override : auto_threads;
+    const int wpc = q.nthreads / 32;
+    q.ndgroups = (d_count + wpc - 1) / wpc;
+    if (q.pack_gl) q.pack_ndg = (d_count + wpc * (32 / q.pack_gl) - 1) / (wpc * (32 / q.pack_gl));
     // Row segmentation, wave-aware: every segment pays ~11 warm-up rows, and the grid runs in waves of (SMs x resident
-    // CTAs) -- with few slices per rank (16 at 8 GPUs) a badly chosen segment count leaves the last wave nearly empty
-    // (4 segments: 576 CTAs over 444 slots = 2 waves; 3 segments: 432 CTAs = 1 wave).  Pick the count that minimises
-    // waves x (rows per segment + warm-up).
-    int best_ns = 1, best_rows = (c->H + 7) & ~7;
+    // CTAs) -- with few slices per rank (16 at 8 GPUs) a badly chosen segment count leaves the last wave nearly empty.
+    // Pick the count that minimises (waves + ragged end) x (rows per segment + warm-up).
+    int best_ns = 1, best_rows = (H + 7) & ~7;
     {
-        int nsm = 148;
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
-        const long slots = (long)nsm * (65536 / (168 * nthreads));        // resident CTAs: 168 registers per thread
+        const long slots = (long)nsm * (65536 / (168 * q.nthreads));        // resident CTAs: 168 registers per thread
         long best_cost = -1;
         for (int want = 1; want <= 12; ++want) {
-            int ns = 1, rows = c->H;
-            plan_segments(c->H, (c->H + want - 1) / want, &ns, &rows);
-            const long ctas = 2L * ns * (P.nstrips * P.ndgroups + P.pack_ndg);
+            int ns = 1, rows = H;
+            plan_segments(H, (H + want - 1) / want, &ns, &rows);
+            const long ctas = 2L * ns * (q.nstrips * q.ndgroups + q.pack_ndg);
             const long waves = (ctas + slots - 1) / slots;
             // the last wave rarely runs full length: count it in proportion to its fill, but never below half a wave
-            const long rem = ctas - (waves - 1) * slots;
-            const double last = rem >= slots ? 1.0 : (0.5 + 0.5 * (double)rem / (double)slots);
+            const long rem_ctas = ctas - (waves - 1) * slots;
+            const double last = rem_ctas >= slots ? 1.0 : (0.5 + 0.5 * (double)rem_ctas / (double)slots);
             // + half a CTA duration: CTAs do not finish in lock-step, and the shorter they are the shorter the ragged end of the
             // kernel.  Fitted on measurements (profiles/r2_segrows_ab2.txt, r2_segrows_shards_ab.txt): C4 -> 4 segments, C3 -> 6,
             // 16 slices of C4 (one of 8 ranks) -> 9, 32 slices of C5 -> 8, each the fastest or within 1 % of it.
@@ -278,6 +276,28 @@ int launch_cvf_stream(psm_ctx* c)
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_ns = ns; best_rows = rows; }
         }
     }
+    q.nseg = best_ns; q.seg_rows = best_rows;
+    if (target_rows > 0) plan_segments(H, target_rows, &q.nseg, &q.seg_rows);
+    q.pack_first = 2 * q.nseg * q.nstrips * q.ndgroups;
+    q.grid = (unsigned)q.pack_first + 2u * q.nseg * q.pack_ndg;
+    return q;
+}
+
+int launch_cvf_stream(psm_ctx* c)
+{
+    CvfParams P;
+    for (int v = 0; v < 2; ++v) { P.vol_in[v] = c->vol[v]; P.vol_out[v] = c->vol_alt[v]; P.guide[v] = c->guide[v]; }
+    P.W = c->W; P.H = c->H; P.Wp = c->Wp; P.Dloc = c->d_count;
+    // the packed remainder needs the tensor-memory ring and no CTA-level staging (variants 1, 2 and 9 keep the plain
+    // decomposition); option 105 = 1 disables it
+    const bool plain_variant = c->cvf_variant == 9 || c->cvf_variant == 2 || (c->cvf_mode != PSM_CVF_MIXED && c->cvf_variant == 1);
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+    const CvfPlan plan = plan_cvf(c->W, c->H, c->d_count, nsm, c->cvf_threads, c->cvf_target_rows,
+                                  !c->cvf_no_pack && !plain_variant && !c->cvf_remap);
+    const int nthreads = plan.nthreads;
+    P.nstrips = plan.nstrips; P.ndgroups = plan.ndgroups; P.nseg = plan.nseg; P.seg_rows = plan.seg_rows;
+    P.pack_gl = plan.pack_gl; P.pack_x0 = plan.pack_x0; P.pack_ndg = plan.pack_ndg; P.pack_first = plan.pack_first;
     P.remap_sms = 0; P.remap_ctas = 0;
     if (c->cvf_remap) {
         int nsm = 0;
@@ -286,8 +306,6 @@ int launch_cvf_stream(psm_ctx* c)
         P.remap_ctas = (int)((227 * 1024) / ((size_t)8 * 4 * nthreads * sizeof(float4) + 1024));  // resident CTAs by shared memory
         if (P.remap_ctas * nthreads * 170 > 65536) P.remap_ctas = 65536 / (nthreads * 170);      // ... and by registers
     }
-    P.nseg = best_ns; P.seg_rows = best_rows;
-    if (c->cvf_target_rows > 0) plan_segments(c->H, c->cvf_target_rows, &P.nseg, &P.seg_rows);
     // kernel selection: mode (exact / mixed) x tuning variant (PSM option 100)
     //   variant 0 (shipped): integer widening + history ring in tensor memory (+ L1 prefetch of the next guide rows in exact mode)
     //   variant 1: F2F conversions, ring in shared memory (the round-1 kernel, kept as the A/B baseline; exact only)
@@ -338,8 +356,7 @@ int launch_cvf_stream(psm_ctx* c)
         PSM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
     P.guide_flags = c->guide_flags;
     P.one = 1.0f; P.mone = -1.0f;
-    P.pack_first = 2 * P.nseg * P.nstrips * P.ndgroups;
-    const unsigned grid = (unsigned)P.pack_first + 2u * P.nseg * P.pack_ndg;
+    const unsigned grid = plan.grid;
     kern<<<grid, nthreads, smem, c->stream>>>(P);
     PSM_LAUNCH_CHECK(c);
     return PSM_OK;
@@ -371,6 +388,15 @@ const char* psm_build_info(void)
 }
 
 const char* psm_last_error(psm_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+int psm_cvf_plan(int width, int height, int d_count, int sm_count, int no_pack, int* out, int n)
+{
+    if (width < 1 || height < 1 || d_count < 1 || sm_count < 1 || !out || n < 10) return PSM_EINVAL;
+    const CvfPlan q = plan_cvf(width, height, d_count, sm_count, 0, 0, !no_pack);
+    const int v[10] = {q.nthreads, q.nstrips, q.ndgroups, q.nseg, q.seg_rows, q.pack_gl, q.pack_x0, q.pack_ndg, q.pack_first, (int)q.grid};
+    for (int i = 0; i < 10; ++i) out[i] = v[i];
+    return PSM_OK;
+}
 
 int psm_create_sharded(psm_ctx** out, int width, int height, int max_disp, int d_begin, int d_count, int device)
 {
