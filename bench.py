@@ -463,6 +463,17 @@ def main():
             "parity": parity,
             "clocks": clocks,
         }
+        if facts and "executed_warp_instructions" in facts:
+            # what actually binds: the instruction stream at 12 warps per SM.  Live: warp instructions of the profiled launch
+            # (committed ncu summary of this workload and mode) / the kernel time measured in THIS run, against 4 warp
+            # instructions per clock per SM at the SM clock sampled in this run.
+            sm_mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+            peak_ips = 148 * 4 * sm_mhz * 1e6
+            ips = facts["executed_warp_instructions"] / (kern_ms * 1e-3)
+            line["roofline"]["issue"] = {"achieved": ips / 1e12, "peak": peak_ips / 1e12, "unit": "T warp-instructions/s",
+                                         "frac": ips / peak_ips, "issue_active_pct_in_profile": facts.get("issue_active_pct"),
+                                         "warps_per_sm": facts.get("warps_per_sm"),
+                                         "note": "instruction count from the committed ncu capture of this workload/mode; time and clock from this run"}
         if mixed is not None:
             mixed["roofline_frac"] = algo_bytes / (mixed["kernel_ms"] * 1e-3) / 1e9 / peak
             line["tolerance_mode"] = mixed

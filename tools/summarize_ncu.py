@@ -100,6 +100,9 @@ def main():
                         f"{float(row['sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'][0]):.0f} / lsu "
                         f"{float(row['sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active'][0]):.0f} %), DRAM "
                         f"{float(row['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'][0]):.0f} % of peak; warp-state samples: {ws}"),
+            "issue_active_pct": float(row["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
+            "executed_warp_instructions": int(float(row["smsp__inst_executed.sum"][0])),
+            "warps_per_sm": round(float(row["sm__warps_active.avg.pct_of_peak_sustained_active"][0]) * 64 / 100, 1),
             "source": f"profiles/r2_cvf_{wl}_mode{mode}_summary.json (ncu --set full, one launch, gpurun)",
         }
     json.dump(facts, open(os.path.join(PROF, "cvf_profile_facts.json"), "w"), indent=1)
